@@ -1,0 +1,123 @@
+"""CPU oracle restatement of the DTQN Q-network forward in plain torch fp32 (test infrastructure only).
+
+Follows dtqn/networks/dtqn.py:158-218, transformer.py:63-78 (post-LN block, ReLU on the sub-layer outputs,
+causal additive -inf mask :49-53), representations.py:17-23,25-52,64-75, position_encodings.py:19-43,
+gates.py:40-41 (ResGate) and utils/torch_utils.py:4-15 (init).  ``nn.MultiheadAttention`` is restated in closed
+form: qkv = x W_in^T + b_in with rows [0:d]=Q, [d:2d]=K, [2d:3d]=V; heads are contiguous d/H
+slices; S = (Q/sqrt(hd)) K^T + mask; P = softmax(S); O = concat_h(P V) W_out^T + b_out; LayerNorm eps 1e-5.
+The functions take a reference-compatible ``state_dict`` (key names of SURVEY.md section 8 a11) so the same weights
+drive the reference module, this oracle and the CUDA path.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def num_layers_of(sd) -> int:
+    n = 0
+    while f"transformer_layers.{n}.layernorm1.weight" in sd:
+        n += 1
+    return n
+
+
+def init_state_dict(obs_dim, num_actions, embed_per_obs_dim, inner_embed, num_heads, num_layers, history_len,
+                    discrete=False, vocab_size=None, pos="learned", generator=None, device="cpu"):
+    """Fresh parameters with the reference's initialisation (utils/torch_utils.py:4-15): N(0, 0.02) for every
+    Linear / Embedding / in_proj / out_proj weight, zero biases, LayerNorm (1, 0), learned position table zeros."""
+    d = inner_embed
+    g = generator
+
+    def nrm(*shape):
+        return torch.empty(*shape, device=device).normal_(0.0, 0.02, generator=g)
+
+    sd = {}
+    if discrete:
+        sd["obs_embedding.observation_embedding.0.weight"] = nrm(vocab_size, embed_per_obs_dim)
+        sd["obs_embedding.observation_embedding.2.weight"] = nrm(d, embed_per_obs_dim * obs_dim)
+        sd["obs_embedding.observation_embedding.2.bias"] = torch.zeros(d, device=device)
+    else:
+        sd["obs_embedding.observation_embedding.weight"] = nrm(d, obs_dim)
+        sd["obs_embedding.observation_embedding.bias"] = torch.zeros(d, device=device)
+    if pos == "sin":
+        position = torch.arange(history_len).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d, 2) * (-math.log(10000.0) / d))
+        pe = torch.zeros(1, history_len, d)
+        pe[0, :, 0::2] = torch.sin(position * div)
+        pe[0, :, 1::2] = torch.cos(position * div)
+        sd["position_embedding.position_encoding"] = pe.to(device)
+    else:
+        sd["position_embedding.position_encoding"] = torch.zeros(1, history_len, d, device=device)
+    mask = torch.triu(torch.ones(history_len, history_len, device=device), diagonal=1)
+    mask[mask.bool()] = -float("inf")
+    for i in range(num_layers):
+        p = f"transformer_layers.{i}."
+        sd[p + "attn_mask"] = mask.clone()
+        sd[p + "layernorm1.weight"] = torch.ones(d, device=device)
+        sd[p + "layernorm1.bias"] = torch.zeros(d, device=device)
+        sd[p + "layernorm2.weight"] = torch.ones(d, device=device)
+        sd[p + "layernorm2.bias"] = torch.zeros(d, device=device)
+        sd[p + "attention.in_proj_weight"] = nrm(3 * d, d)
+        sd[p + "attention.in_proj_bias"] = torch.zeros(3 * d, device=device)
+        sd[p + "attention.out_proj.weight"] = nrm(d, d)
+        sd[p + "attention.out_proj.bias"] = torch.zeros(d, device=device)
+        sd[p + "ffn.0.weight"] = nrm(4 * d, d)
+        sd[p + "ffn.0.bias"] = torch.zeros(4 * d, device=device)
+        sd[p + "ffn.2.weight"] = nrm(d, 4 * d)
+        sd[p + "ffn.2.bias"] = torch.zeros(d, device=device)
+    sd["ffn.0.weight"] = nrm(d, d)
+    sd["ffn.0.bias"] = torch.zeros(d, device=device)
+    sd["ffn.2.weight"] = nrm(num_actions, d)
+    sd["ffn.2.bias"] = torch.zeros(num_actions, device=device)
+    return sd
+
+
+def embed(sd, obss):
+    """representations.py:17-23 (+ :47-51 discrete, :74 continuous).  obss [B,L,O] float (continuous) or int."""
+    if "obs_embedding.observation_embedding.0.weight" in sd:
+        e = sd["obs_embedding.observation_embedding.0.weight"][obss.long()]          # [B,L,O,E]
+        e = e.flatten(start_dim=-2)                                                   # nn.Flatten(-2)
+        return e @ sd["obs_embedding.observation_embedding.2.weight"].T + sd["obs_embedding.observation_embedding.2.bias"]
+    return obss.float() @ sd["obs_embedding.observation_embedding.weight"].T + sd["obs_embedding.observation_embedding.bias"]
+
+
+def layer_forward(sd, prefix, x, num_heads):
+    """transformer.py:63-78."""
+    B, L, d = x.shape
+    hd = d // num_heads
+    qkv = x @ sd[prefix + "attention.in_proj_weight"].T + sd[prefix + "attention.in_proj_bias"]
+    q, k, v = qkv.split(d, dim=-1)
+    q = q.view(B, L, num_heads, hd).transpose(1, 2) / math.sqrt(hd)
+    k = k.view(B, L, num_heads, hd).transpose(1, 2)
+    v = v.view(B, L, num_heads, hd).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) + sd[prefix + "attn_mask"][:L, :L]
+    o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, L, d)
+    a = o @ sd[prefix + "attention.out_proj.weight"].T + sd[prefix + "attention.out_proj.bias"]
+    x = F.layer_norm(x + torch.relu(a), (d,), sd[prefix + "layernorm1.weight"], sd[prefix + "layernorm1.bias"], 1e-5)
+    h = torch.relu(x @ sd[prefix + "ffn.0.weight"].T + sd[prefix + "ffn.0.bias"])
+    f = h @ sd[prefix + "ffn.2.weight"].T + sd[prefix + "ffn.2.bias"]
+    return F.layer_norm(x + torch.relu(f), (d,), sd[prefix + "layernorm2.weight"], sd[prefix + "layernorm2.bias"], 1e-5)
+
+
+def forward(sd, obss, num_heads):
+    """dtqn.py:158-218 with action_dim = 0, bag_size = 0, dropout = 0 (run.py defaults :98-103,151-153,173-175)."""
+    L = obss.shape[1]
+    assert L <= sd["position_embedding.position_encoding"].shape[1], "Cannot forward, history is longer than expected."
+    x = embed(sd, obss) + sd["position_embedding.position_encoding"][:, :L, :]
+    for i in range(num_layers_of(sd)):
+        x = layer_forward(sd, f"transformer_layers.{i}.", x, num_heads)
+    h = torch.relu(x @ sd["ffn.0.weight"].T + sd["ffn.0.bias"])
+    return h @ sd["ffn.2.weight"].T + sd["ffn.2.bias"]
+
+
+def trainable_keys(sd, pos="learned"):
+    """Keys that receive gradients: everything but attn_mask (requires_grad=False, transformer.py:49-53) and a
+    non-learned position table (position_encodings.py:35,49-51), in state_dict order."""
+    ks = []
+    for k in sd:
+        if k.endswith("attn_mask"):
+            continue
+        if k == "position_embedding.position_encoding" and pos != "learned":
+            continue
+        ks.append(k)
+    return ks

@@ -1,0 +1,6 @@
+class Error(Exception):
+    pass
+
+
+class UnregisteredEnv(Error):
+    pass

@@ -1,0 +1,1 @@
+from gym.utils import seeding

@@ -1,0 +1,238 @@
+"""Generate the golden fixtures by EXECUTING the unmodified reference (kevslinger/DTQN) in the build container.
+
+    python tests/golden/gen_golden.py          # needs /root/reference; writes tests/golden/*.npz
+
+The reference has no tests / golden vectors of its own, so these fixtures are what pins the oracle
+port (``oracle/``) and, through it, the CUDA path.  They travel to the GPU box; /root/reference does not.
+Everything here goes through ``oracle.ref_harness`` (stub gym/pyglet + two compatibility shims, no reference file
+is modified).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_harness as rh  # noqa: E402
+
+rh.activate()
+import gym  # noqa: E402  (stub)
+
+ENV_SHAPES = {"DiscreteCarFlag-v0": (3, 3), "Memory-5-v0": (10, 10)}
+
+
+def action_tapes(env_id, n_seeds, T, rng):
+    A = ENV_SHAPES[env_id][1]
+    tapes = rng.integers(0, A, size=(n_seeds, T)).astype(np.uint8)
+    if env_id == "DiscreteCarFlag-v0":
+        tapes[0, :] = 2          # drive right: terminates at +1 (heaven or hell)
+        tapes[1, :] = 1          # coast: 200-step TimeLimit truncation
+        tapes[2, :] = 0          # drive left
+        tapes[3, : T // 2] = 2   # mixed
+    else:
+        tapes[0, :] = 0          # repeatedly pick card 0
+        tapes[1, :] = np.arange(T) % A
+    return tapes
+
+
+def gen_env(env_id, n_seeds, T, first_seed=1):
+    rng = np.random.default_rng(1234)
+    O, _ = ENV_SHAPES[env_id]
+    tapes = action_tapes(env_id, n_seeds, T, rng)
+    seeds = np.arange(first_seed, first_seed + n_seeds, dtype=np.int64)
+    out = dict(seeds=seeds, actions=tapes,
+               initial_obs=np.zeros((n_seeds, O)), obs=np.zeros((n_seeds, T, O)), reward=np.zeros((n_seeds, T)),
+               done=np.zeros((n_seeds, T), bool), truncated=np.zeros((n_seeds, T), bool),
+               success=np.zeros((n_seeds, T), bool),
+               reset_obs=np.full((n_seeds, T, O), np.nan), rng_state=np.zeros((n_seeds, 6), np.uint64))
+    for i, seed in enumerate(seeds):
+        env = gym.make(env_id)
+        env.seed(int(seed))
+        out["initial_obs"][i] = env.reset()
+        for t in range(T):
+            o, r, d, info = env.step(int(tapes[i, t]))
+            out["obs"][i, t], out["reward"][i, t], out["done"][i, t] = o, r, d
+            out["truncated"][i, t] = bool(info.get("TimeLimit.truncated", False))
+            out["success"][i, t] = bool(info.get("is_success", False))
+            if d:
+                out["reset_obs"][i, t] = env.reset()
+        st = env.unwrapped.np_random.bit_generator.state
+        M = (1 << 64) - 1
+        out["rng_state"][i] = [st["state"]["state"] >> 64, st["state"]["state"] & M, st["state"]["inc"] >> 64,
+                               st["state"]["inc"] & M, st["has_uint32"], st["uinteger"]]
+    return out
+
+
+def perturb(net, gen):
+    """Make every parameter non-trivial (the init has zero biases / zero position table / unit LayerNorm)."""
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("attn_mask"):
+                continue
+            if name.endswith("bias") or "position_encoding" in name:
+                p.add_(torch.empty_like(p).normal_(0, 0.05, generator=gen))
+            elif "layernorm" in name and name.endswith("weight"):
+                p.add_(torch.empty_like(p).normal_(0, 0.1, generator=gen))
+            else:
+                p.mul_(3.0)   # larger weights -> O(1) Q values, harder numerics than the 0.02 init
+
+
+def make_agent(env_id, inner_embed, layers, context, batch, seed=1, heads=8, history=None, buf=50_000):
+    from utils import agent_utils
+    env = gym.make(env_id)
+    rh.set_global_seed(seed, env)
+    agent = agent_utils.get_agent("DTQN", [env], 8, 0, inner_embed, buf, torch.device("cpu"), 3e-4, batch, context,
+                                  -1, history or context, 10_000, 0.99, num_heads=heads, num_layers=layers,
+                                  dropout=0.0, identity=False, gate="res", pos="learned", bag_size=0)
+    rh.widen_episode_lengths(agent)
+    return agent, env
+
+
+def sd_np(sd, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def gen_train(env_id, inner_embed, layers, context, batch, prepop, n_steps, tag):
+    """Reference DtqnAgent.train() on injected batches: Q, loss, grads (step 1) and post-Adam parameters."""
+    sys.argv = ["run.py"]
+    import run as ref_run
+    import random
+
+    agent, env = make_agent(env_id, inner_embed, layers, context, batch)
+    gen = torch.Generator().manual_seed(7)
+    perturb(agent.policy_network, gen)
+    agent.target_update()
+    with torch.no_grad():   # make the target differ from the policy so a* and Q_tgt are distinguishable
+        for name, p in agent.target_network.named_parameters():
+            if not name.endswith("attn_mask"):
+                p.add_(torch.empty_like(p).normal_(0, 0.01, generator=gen))
+    ref_run.prepopulate(agent, prepop, [env])
+    out = {}
+    out.update(sd_np(agent.policy_network.state_dict(), "policy0/"))
+    out.update(sd_np(agent.target_network.state_dict(), "target0/"))
+    rb = agent.replay_buffer
+    # the replay arrays after prepopulate (only the filled part) pin the store/flush layout
+    n_ep = min(rb.pos[0], rb.max_size)
+    out["replay/obss"], out["replay/actions"] = rb.obss[:n_ep].copy(), rb.actions[:n_ep].copy()
+    out["replay/rewards"], out["replay/dones"] = rb.rewards[:n_ep].copy(), rb.dones[:n_ep].copy()
+    out["replay/episode_lengths"] = rb.episode_lengths[:n_ep].copy()
+    out["replay/pos"] = np.array(rb.pos)
+    random.seed(99)
+    real_sample = rb.sample
+    for s in range(n_steps):
+        state = random.getstate()
+        batch_np = real_sample(batch)
+        # recover the (episode, start) indices of this draw by replaying the same `random` stream
+        random.setstate(state)
+        valid = [i for i in range(min(rb.pos[0], rb.max_size)) if i != rb.pos[0] % rb.max_size]
+        eps = np.array([random.choice(valid) for _ in range(batch)])
+        starts = np.array([random.randint(0, max(0, int(rb.episode_lengths[e]) - rb.context_len)) for e in eps])
+        out[f"step{s}/episodes"], out[f"step{s}/starts"] = eps, starts
+        for name, arr in zip(("obss", "actions", "rewards", "next_obss", "next_actions", "dones", "eplens"), batch_np):
+            out[f"step{s}/{name}"] = np.asarray(arr).copy()
+        rb.sample = lambda bs, b=batch_np: b
+        if s == 0:
+            with torch.no_grad():
+                ot = torch.as_tensor(batch_np[0], dtype=agent.obs_tensor_type)
+                nt = torch.as_tensor(batch_np[3], dtype=agent.obs_tensor_type)
+                out["step0/q_policy_obs"] = agent.policy_network(ot).numpy().copy()
+                out["step0/q_policy_next"] = agent.policy_network(nt).numpy().copy()
+                out["step0/q_target_next"] = agent.target_network(nt).numpy().copy()
+        # capture the raw (unclipped) gradients: clip_grad_norm_ scales .grad in place, so hook backward
+        raw = {}
+        hooks = [p.register_hook(lambda g, n=n: raw.__setitem__(n, g.detach().clone()))
+                 for n, p in agent.policy_network.named_parameters() if p.requires_grad]
+        agent.train()
+        for h in hooks:
+            h.remove()
+        if s == 0:
+            for n, g in raw.items():
+                out["step0/grad/" + n] = g.numpy().copy()
+        rb.sample = real_sample
+    stats = {}
+    for nm in ("td_errors", "grad_norms", "qvalue_max", "qvalue_mean", "qvalue_min", "target_max", "target_mean", "target_min"):
+        ra = getattr(agent, nm)
+        vals = list(getattr(ra, "record", getattr(ra, "q", getattr(ra, "values", []))))
+        stats[nm] = np.array(vals, dtype=np.float64)
+    for k, v in stats.items():
+        out["stats/" + k] = v
+    out.update(sd_np(agent.policy_network.state_dict(), f"policy{n_steps}/"))
+    out["meta"] = np.array([inner_embed, layers, context, batch, 8, n_steps])
+    np.savez_compressed(os.path.join(HERE, f"train_{tag}.npz"), **out)
+    print("wrote", f"train_{tag}.npz", {k: v.shape for k, v in stats.items()})
+
+
+def gen_forward_short(env_id, inner_embed, layers, context, tag):
+    """DTQN.forward on sequences shorter than the context (acting path, dtqn/agents/dtqn.py:81-107)."""
+    agent, env = make_agent(env_id, inner_embed, layers, context, 32)
+    gen = torch.Generator().manual_seed(11)
+    perturb(agent.policy_network, gen)
+    O, A = ENV_SHAPES[env_id]
+    out = sd_np(agent.policy_network.state_dict(), "policy/")
+    for L in (1, 7, context):
+        if env_id == "Memory-5-v0":
+            x = torch.randint(0, 9, (5, L, O), generator=gen)
+        else:
+            x = torch.empty(5, L, O).uniform_(-1.1, 1.1, generator=gen)
+            x[:, :, 2] = torch.randint(-1, 2, (5, L), generator=gen).float()
+        with torch.no_grad():
+            q = agent.policy_network(x)
+        out[f"L{L}/obss"], out[f"L{L}/q"] = x.numpy(), q.numpy()
+    out["meta"] = np.array([inner_embed, layers, context, 8])
+    np.savez_compressed(os.path.join(HERE, f"forward_{tag}.npz"), **out)
+    print("wrote", f"forward_{tag}.npz")
+
+
+def gen_acting(env_id, inner_embed, context, steps, tag):
+    """The reference acting loop (run.step, run.py:356-377) with epsilon = 0.3: records the env/obs/action stream,
+    the Context window fed to the network and the greedy Q of every step -> pins Context + get_action semantics."""
+    sys.argv = ["run.py"]
+    import run as ref_run
+    from utils.random import RNG
+    from utils import epsilon_anneal
+
+    agent, env = make_agent(env_id, inner_embed, 2, context, 32)
+    gen = torch.Generator().manual_seed(5)
+    perturb(agent.policy_network, gen)
+    eps = epsilon_anneal.Constant(0.3)
+    agent.eval_off()
+    agent.context_reset(env.reset())
+    O, A = ENV_SHAPES[env_id]
+    rec = dict(ctx_obs=[], ctx_len=[], action=[], obs=[], reward=[], done=[], buffer_done=[], greedy_q=[])
+    for t in range(steps):
+        n = min(agent.context.max_length, agent.context.timestep + 1)
+        win = np.full((context, O), np.nan)
+        win[:n] = agent.context.obs[:n]
+        rec["ctx_obs"].append(win)
+        rec["ctx_len"].append(n)
+        with torch.no_grad():
+            q = agent.policy_network(torch.as_tensor(agent.context.obs[:n], dtype=agent.obs_tensor_type).unsqueeze(0))
+        rec["greedy_q"].append(q[0, -1].numpy().copy())
+        action = agent.get_action(epsilon=eps.val)
+        next_obs, reward, done, info = env.step(action)
+        buffer_done = False if info.get("TimeLimit.truncated", False) else done
+        agent.observe(next_obs, action, reward, buffer_done)
+        rec["action"].append(action); rec["obs"].append(np.array(next_obs, dtype=np.float64))
+        rec["reward"].append(reward); rec["done"].append(done); rec["buffer_done"].append(buffer_done)
+        if done:
+            agent.replay_buffer.flush()
+            agent.context_reset(env.reset())
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(sd_np(agent.policy_network.state_dict(), "policy/"))
+    out["meta"] = np.array([inner_embed, 2, context, 8])
+    np.savez_compressed(os.path.join(HERE, f"acting_{tag}.npz"), **out)
+    print("wrote", f"acting_{tag}.npz")
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "env_carflag.npz"), **gen_env("DiscreteCarFlag-v0", 24, 700))
+    np.savez_compressed(os.path.join(HERE, "env_memory.npz"), **gen_env("Memory-5-v0", 24, 400))
+    print("wrote env fixtures")
+    gen_forward_short("DiscreteCarFlag-v0", 64, 2, 50, "carflag")
+    gen_forward_short("Memory-5-v0", 128, 2, 50, "memory")
+    gen_train("DiscreteCarFlag-v0", 64, 2, 50, 32, 12000, 3, "carflag")
+    gen_train("Memory-5-v0", 128, 1, 50, 8, 1500, 2, "memory")
+    gen_acting("DiscreteCarFlag-v0", 64, 50, 260, "carflag")
