@@ -1,0 +1,93 @@
+// fp32 CUDA-core GEMM tile used for the small / latency-bound contractions of the DTQN hot path (train batch of
+// 32 x 50 tokens, K = 64..512) and for every backward GEMM.  64 x BN output tile per 256-thread CTA, BK = 16,
+// register prefetch of the next k-slab, conflict-free float4 shared-memory reads.
+//   NT:  C[M,N] = A[M,K] * W[N,K]^T   (forward Linear: x W^T)            B_NN = false
+//   NN:  C[M,N] = A[M,K] * B[K,N]     (dgrad: dY W)                      B_NN = true
+#pragma once
+#include "common.cuh"
+
+#define GEMM_BM 64
+#define GEMM_BK 16
+#define GEMM_THREADS 256
+
+template <int BN>
+struct GemmSmem {
+    float As[GEMM_BK][GEMM_BM + 4];
+    float Bs[GEMM_BK][BN + 4];
+};
+
+// acc[i][j] <-> row m0 + ty*4 + i, col n0 + gemm_col(tx, j), with ty = tid / 16, tx = tid % 16: each thread owns groups
+// of 4 contiguous columns 64 apart, so the float4 reads of a B slab row are contiguous across the half-warp.
+__device__ __forceinline__ int gemm_col(int tx, int j) { return (j >> 2) * 64 + tx * 4 + (j & 3); }
+
+template <int BN, bool B_NN>
+__device__ __forceinline__ void gemm_tile_64(const float* __restrict__ A, int lda, int M,
+                                             const float* __restrict__ B, int ldb, int K, int m0, int n0,
+                                             float (&acc)[4][BN / 16], GemmSmem<BN>& sm) {
+    constexpr int TN = BN / 16;
+    constexpr int BV = BN / 64;                 // float4 loads of the B slab per thread
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    // A slab: 64 rows x 16 k  -> one float4 (along k) per thread
+    const int a_row = tid >> 2, a_kq = tid & 3;
+    const bool a_ok = (m0 + a_row) < M;
+    const float* a_ptr = A + (size_t)(m0 + a_row) * lda + a_kq * 4;
+    float4 a_reg, b_reg[BV];
+    auto load_slab = [&](int k0) {
+        a_reg = a_ok ? *reinterpret_cast<const float4*>(a_ptr + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < BV; ++v) {
+            const int idx = tid + v * GEMM_THREADS;
+            if (B_NN) {   // B[k0 + kr, n0 + nq*4 ..]  (16 x BN slab, N contiguous)
+                const int kr = idx / (BN / 4), nq = idx % (BN / 4);
+                b_reg[v] = *reinterpret_cast<const float4*>(B + (size_t)(k0 + kr) * ldb + n0 + nq * 4);
+            } else {      // W[n0 + nr, k0 + kq*4 ..]  (BN x 16 slab, K contiguous)
+                const int nr = idx >> 2, kq = idx & 3;
+                b_reg[v] = *reinterpret_cast<const float4*>(B + (size_t)(n0 + nr) * ldb + k0 + kq * 4);
+            }
+        }
+    };
+    auto store_slab = [&]() {
+        sm.As[a_kq * 4 + 0][a_row] = a_reg.x; sm.As[a_kq * 4 + 1][a_row] = a_reg.y;
+        sm.As[a_kq * 4 + 2][a_row] = a_reg.z; sm.As[a_kq * 4 + 3][a_row] = a_reg.w;
+#pragma unroll
+        for (int v = 0; v < BV; ++v) {
+            const int idx = tid + v * GEMM_THREADS;
+            if (B_NN) {
+                const int kr = idx / (BN / 4), nq = idx % (BN / 4);
+                *reinterpret_cast<float4*>(&sm.Bs[kr][nq * 4]) = b_reg[v];
+            } else {
+                const int nr = idx >> 2, kq = idx & 3;
+                sm.Bs[kq * 4 + 0][nr] = b_reg[v].x; sm.Bs[kq * 4 + 1][nr] = b_reg[v].y;
+                sm.Bs[kq * 4 + 2][nr] = b_reg[v].z; sm.Bs[kq * 4 + 3][nr] = b_reg[v].w;
+            }
+        }
+    };
+    load_slab(0);
+    for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+        store_slab();
+        __syncthreads();
+        if (k0 + GEMM_BK < K) load_slab(k0 + GEMM_BK);
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&sm.As[kk][ty * 4]);
+            const float a[4] = {av.x, av.y, av.z, av.w};
+            float b[TN];
+#pragma unroll
+            for (int j4 = 0; j4 < TN / 4; ++j4) {
+                const float4 bv = *reinterpret_cast<const float4*>(&sm.Bs[kk][j4 * 64 + tx * 4]);
+                b[j4 * 4 + 0] = bv.x; b[j4 * 4 + 1] = bv.y; b[j4 * 4 + 2] = bv.z; b[j4 * 4 + 3] = bv.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+}

@@ -1,0 +1,91 @@
+// Parameter / workspace layout of the DTQN Q-network shared by the forward, backward and optimiser kernels.
+// Mirrors the module tree of dtqn/networks/dtqn.py:41-156 (state_dict names in SURVEY.md section 8 a11).
+#pragma once
+#include "common.cuh"
+
+#define DTQN_MAX_LAYERS 8
+#define DTQN_MAX_GROUPS 3
+
+// offsets (in floats) into the flat parameter buffer; every tensor starts on a 16-byte boundary
+struct LayerOff {
+    long long ln1_w, ln1_b, ln2_w, ln2_b, in_w, in_b, out_w, out_b, f1_w, f1_b, f2_w, f2_b;
+};
+struct NetLayout {
+    long long emb_table;   // [vocab, e]   (discrete only, else -1)   obs_embedding.observation_embedding.0.weight
+    long long emb_w;       // [d, K_in]    ...observation_embedding(.2).weight
+    long long emb_b;       // [d]
+    long long pos;         // [ctx, d]     position_embedding.position_encoding
+    LayerOff layer[DTQN_MAX_LAYERS];
+    long long h1_w, h1_b;  // ffn.0  [d,d], [d]
+    long long h2_w, h2_b;  // ffn.2  [A,d], [A]
+    long long total;       // floats, padded
+    int k_in;              // O (continuous) or O*e (discrete)
+};
+
+static inline long long al4(long long x) { return (x + 3) & ~3ll; }
+
+static inline int net_layout(const dtqn_net_cfg& c, NetLayout& L) {
+    if (c.n_layers < 1 || c.n_layers > DTQN_MAX_LAYERS) return DTQN_E_ARG;
+    if (c.d_model != 64 && c.d_model != 128) return DTQN_E_UNSUPPORTED;
+    if (c.n_heads <= 0 || c.d_model % c.n_heads || (c.d_model / c.n_heads) > 32 || (c.d_model / c.n_heads) % 4)
+        return DTQN_E_UNSUPPORTED;
+    if (c.context_len < 1 || c.context_len > 128 || c.obs_dim < 1 || c.obs_dim > 16 || c.num_actions < 1 ||
+        c.num_actions > 32) return DTQN_E_UNSUPPORTED;
+    if (c.discrete && (c.vocab < 1 || c.vocab > 64 || c.embed_per_obs < 1 || c.embed_per_obs > 16)) return DTQN_E_UNSUPPORTED;
+    const long long d = c.d_model;
+    long long o = 0;
+    L.k_in = c.discrete ? c.obs_dim * c.embed_per_obs : c.obs_dim;
+    if (c.discrete) { L.emb_table = o; o = al4(o + (long long)c.vocab * c.embed_per_obs); } else L.emb_table = -1;
+    L.emb_w = o; o = al4(o + d * L.k_in);
+    L.emb_b = o; o = al4(o + d);
+    L.pos = o;   o = al4(o + (long long)c.context_len * d);
+    for (int i = 0; i < c.n_layers; ++i) {
+        LayerOff& l = L.layer[i];
+        l.ln1_w = o; o += d; l.ln1_b = o; o += d; l.ln2_w = o; o += d; l.ln2_b = o; o += d;
+        l.in_w = o; o += 3 * d * d; l.in_b = o; o += 3 * d;
+        l.out_w = o; o += d * d;    l.out_b = o; o += d;
+        l.f1_w = o; o += 4 * d * d; l.f1_b = o; o += 4 * d;
+        l.f2_w = o; o += 4 * d * d; l.f2_b = o; o += d;
+    }
+    L.h1_w = o; o += d * d; L.h1_b = o; o += d;
+    L.h2_w = o; o = al4(o + (long long)c.num_actions * d);
+    L.h2_b = o; o = al4(o + c.num_actions);
+    L.total = o;
+    return 0;
+}
+
+// Activation workspace (floats) for G groups x n_seq sequences x L tokens.  With save = 1 every layer keeps its own
+// buffers (needed by the backward pass); with save = 0 the per-layer buffers alias one set.
+struct LayerAct {
+    float *qkv, *o, *r1, *st1, *x1, *h, *r2, *st2, *x2;
+};
+struct NetAct {
+    float* x0;
+    LayerAct layer[DTQN_MAX_LAYERS];
+    float* hh;
+    float* q;      // [T, A]
+    long long total;
+};
+
+static inline long long net_act_layout(const dtqn_net_cfg& c, long long T, int save, float* base, NetAct& A) {
+    const long long d = c.d_model;
+    long long o = 0;
+    auto take = [&](long long n) { float* p = base ? base + o : nullptr; o = al4(o + n); return p; };
+    A.x0 = take(T * d);
+    for (int i = 0; i < c.n_layers; ++i) {
+        if (i == 0 || save) {
+            LayerAct& l = A.layer[i];
+            l.qkv = take(T * 3 * d); l.o = take(T * d); l.r1 = take(T * d); l.st1 = take(T * 2); l.x1 = take(T * d);
+            l.h = take(T * 4 * d);   l.r2 = take(T * d); l.st2 = take(T * 2);
+            l.x2 = take(T * d);
+        } else {
+            A.layer[i] = A.layer[i - 1];
+            // ping-pong the layer output so a layer never writes the buffer it reads as its input
+            A.layer[i].x2 = (i & 1) ? A.x0 : A.layer[0].x2;
+        }
+    }
+    A.hh = take(T * d);
+    A.q = take(T * c.num_actions);
+    A.total = o;
+    return o;
+}

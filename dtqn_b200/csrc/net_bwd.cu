@@ -1,0 +1,509 @@
+// Double-DQN sequence TD loss and the DTQN backward pass (dtqn/agents/dtqn.py:215-256: gather Q(s,a), a* = argmax
+// policy(s'), Q_tgt(s',a*), Bellman target, mse_loss over the last `history` positions, loss.backward()).
+// All gradients are derived by hand for the forward in net_fwd.cu; parity is against torch autograd on the oracle.
+#include "net.cuh"
+#include "gemm_simt.cuh"
+
+namespace {
+
+// ---- TD loss: emits dLoss/dQ directly + the logged statistics (agents/dtqn.py:245-253) --------------------------------
+// q_all [3, B, L, A]: 0 = policy(obs), 1 = policy(next_obs), 2 = target(next_obs).
+__global__ void __launch_bounds__(256)
+td_loss_kernel(const float* __restrict__ q_all, const uint8_t* __restrict__ act_win, const float* __restrict__ rew,
+               const uint8_t* __restrict__ done, int B, int L, int A, int history, float gamma,
+               float* __restrict__ dq, float* __restrict__ partial, unsigned* __restrict__ ticket,
+               float* __restrict__ stats) {
+    const long long T = (long long)B * L;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float se = 0.f, qs = 0.f, ys = 0.f, qmx = -INFINITY, qmn = INFINITY, ymx = -INFINITY, ymn = INFINITY;
+    if (t < T) {
+        const int b = (int)(t / L), l = (int)(t % L);
+        const int a = act_win[(long long)b * (L + 1) + l];
+        const float* q0 = q_all + t * A;
+        const float* q1 = q_all + (T + t) * A;
+        const float* q2 = q_all + (2 * T + t) * A;
+        int astar = 0; float best = q1[0];
+        for (int k = 1; k < A; ++k) { const float v = q1[k]; if (v > best) { best = v; astar = k; } }   // torch.argmax
+        const float qsel = q0[a];
+        const float y = rew[t] + (1.f - (float)done[t]) * (q2[astar] * gamma);                          // :236-238
+        const bool in_hist = l >= L - history;                                                          // :240-241
+        const float diff = qsel - y;
+        for (int k = 0; k < A; ++k) dq[t * A + k] = 0.f;
+        if (in_hist) {
+            dq[t * A + a] = 2.f * diff / (float)((long long)B * history);                              // d mse / dq
+            se = diff * diff; qs = qsel; ys = y; qmx = qmn = qsel; ymx = ymn = y;
+        }
+    }
+    // block reduction (fixed order) -> per-block partials -> last block finalises in block order (deterministic)
+    __shared__ float red[7][8];
+    float v[7] = {se, qs, ys, qmx, qmn, ymx, ymn};
+    v[0] = warp_sum(v[0]); v[1] = warp_sum(v[1]); v[2] = warp_sum(v[2]);
+    v[3] = warp_max(v[3]); v[4] = warp_min(v[4]); v[5] = warp_max(v[5]); v[6] = warp_min(v[6]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) for (int k = 0; k < 7; ++k) red[k][warp] = v[k];
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        float r[7] = {0.f, 0.f, 0.f, -INFINITY, INFINITY, -INFINITY, INFINITY};
+        for (int w = 0; w < 8; ++w) {
+            r[0] += red[0][w]; r[1] += red[1][w]; r[2] += red[2][w];
+            r[3] = fmaxf(r[3], red[3][w]); r[4] = fminf(r[4], red[4][w]);
+            r[5] = fmaxf(r[5], red[5][w]); r[6] = fminf(r[6], red[6][w]);
+        }
+        for (int k = 0; k < 7; ++k) partial[blockIdx.x * 8 + k] = r[k];
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float r[7] = {0.f, 0.f, 0.f, -INFINITY, INFINITY, -INFINITY, INFINITY};
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) {
+            const volatile float* pp = partial + bb * 8;
+            r[0] += pp[0]; r[1] += pp[1]; r[2] += pp[2];
+            r[3] = fmaxf(r[3], pp[3]); r[4] = fminf(r[4], pp[4]); r[5] = fmaxf(r[5], pp[5]); r[6] = fminf(r[6], pp[6]);
+        }
+        const float n = (float)((long long)B * history);
+        stats[0] = r[0] / n;              // F.mse_loss (mean)
+        stats[1] = r[3]; stats[2] = r[1] / n; stats[3] = r[4];
+        stats[4] = r[5]; stats[5] = r[2] / n; stats[6] = r[6];
+        *ticket = 0u;
+    }
+}
+
+// ---- head (ffn.2) backward: N = A is tiny -> CUDA cores --------------------------------------------------------------------
+// d_hh = (dq W2) * [hh > 0];  dW2 += dq^T hh;  db2 += colsum(dq).   64 tokens per CTA.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, const float* __restrict__ W2, int T, int d,
+                int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2) {
+    __shared__ float sdq[64][33];
+    const int t0 = blockIdx.x * 64;
+    const int nt = min(64, T - t0);
+    for (int e = threadIdx.x; e < 64 * A; e += blockDim.x) {
+        const int r = e / A, a = e % A;
+        sdq[r][a] = r < nt ? dq[(long long)(t0 + r) * A + a] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nt * d; e += blockDim.x) {
+        const int r = e / d, c = e % d;
+        float s = 0.f;
+        for (int a = 0; a < A; ++a) s = fmaf(sdq[r][a], __ldg(W2 + a * d + c), s);
+        const long long gi = (long long)(t0 + r) * d + c;
+        d_hh[gi] = hh[gi] > 0.f ? s : 0.f;
+    }
+    for (int e = threadIdx.x; e < A * d; e += blockDim.x) {
+        const int a = e / d, c = e % d;
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s = fmaf(sdq[r][a], hh[(long long)(t0 + r) * d + c], s);
+        atomicAdd(gW2 + a * d + c, s);
+    }
+    if (threadIdx.x < A) {
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s += sdq[r][threadIdx.x];
+        atomicAdd(gb2 + threadIdx.x, s);
+    }
+}
+
+// ---- dgrad:  dX[T, Kf] = dY[T, Nf] W[Nf, Kf]  (+ epilogue) -----------------------------------------------------------------
+enum { DG_NONE = 0, DG_MASK = 1, DG_ADD = 2 };
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS)
+dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ aux,
+             float* __restrict__ dX, int T, int Nf, int Kf) {
+    __shared__ GemmSmem<BN> sm;
+    constexpr int TN = BN / 16;
+    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+    float acc[4][TN];
+    gemm_tile_64<BN, true>(dY, Nf, T, W, Kf, Nf, m0, n0, acc, sm);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty * 4 + i;
+        if (r >= T) continue;
+#pragma unroll
+        for (int j4 = 0; j4 < TN / 4; ++j4) {
+            const size_t off = (size_t)r * Kf + n0 + j4 * 64 + tx * 4;
+            float v[4] = {acc[i][j4 * 4], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]};
+            if (EPI != DG_NONE) {
+                const float4 x = *reinterpret_cast<const float4*>(aux + off);
+                const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = (EPI == DG_MASK) ? (xv[q] > 0.f ? v[q] : 0.f) : v[q] + xv[q];
+            }
+            *reinterpret_cast<float4*>(dX + off) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ---- wgrad:  gW[Nf, Kf] += dY[T, Nf]^T X[T, Kf];  gb[Nf] += colsum(dY) --------------------------------------------------------
+// 64 x 64 tile of gW per CTA, tokens split over gridDim.z chunks, fp32 atomics into the (zeroed) flat gradient.
+#define WG_CHUNK 256
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int Nf, int Kf,
+             float* __restrict__ gW, float* __restrict__ gb) {
+    __shared__ float As[16][64 + 4];   // dY slab: 16 tokens x 64 n
+    __shared__ float Bs[16][64 + 4];   // X  slab: 16 tokens x 64 k
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int tb = blockIdx.z * WG_CHUNK, te = min(T, tb + WG_CHUNK);
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int lr = tid >> 4, lc = (tid & 15) * 4;            // slab load: row lr (token), 4 columns at lc
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    for (int t = tb; t < te; t += 16) {
+        const bool ok = (t + lr) < te;
+        const float4 av = ok ? *reinterpret_cast<const float4*>(dY + (size_t)(t + lr) * Nf + n0 + lc) : make_float4(0, 0, 0, 0);
+        const float4 bv = ok ? *reinterpret_cast<const float4*>(X + (size_t)(t + lr) * Kf + k0 + lc) : make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(&As[lr][lc]) = av;
+        *reinterpret_cast<float4*>(&Bs[lr][lc]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (gb && blockIdx.y == 0 && tid < 64) {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) bsum += As[kk][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(gW + (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4 + j, acc[i][j]);
+    if (gb && blockIdx.y == 0 && tid < 64) atomicAdd(gb + n0 + tid, bsum);
+}
+
+// ---- LayerNorm backward fused with the ReLU / residual split (transformer.py:72-73,76-77) -----------------------------------
+//   y = LN(u), u = x_in + r, r = relu(a).   Given dy: du (-> residual path) and da = du * [r > 0]; dgamma, dbeta.
+template <int D>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xin, const float* __restrict__ r,
+              const float* __restrict__ st, const float* __restrict__ gamma, int T, float* __restrict__ du,
+              float* __restrict__ da, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    constexpr int PER = D / 32, ROWS = 4;                     // rows per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float gam[PER], ag[PER], ab[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { gam[k] = gamma[lane + 32 * k]; ag[k] = 0.f; ab[k] = 0.f; }
+    const int row0 = (blockIdx.x * 8 + warp) * ROWS;
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const int t = row0 + rr;
+        if (t >= T) break;
+        const float mean = st[2 * t], rstd = st[2 * t + 1];
+        float xh[PER], g[PER], rv[PER], dyv[PER];
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const size_t o = (size_t)t * D + lane + 32 * k;
+            rv[k] = r[o]; dyv[k] = dy[o];
+            xh[k] = (xin[o] + rv[k] - mean) * rstd;
+            g[k] = dyv[k] * gam[k];
+            m1 += g[k]; m2 = fmaf(g[k], xh[k], m2);
+            ag[k] = fmaf(dyv[k], xh[k], ag[k]); ab[k] += dyv[k];
+        }
+        m1 = warp_sum(m1) * (1.f / D); m2 = warp_sum(m2) * (1.f / D);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const size_t o = (size_t)t * D + lane + 32 * k;
+            const float v = rstd * (g[k] - m1 - xh[k] * m2);
+            du[o] = v;
+            da[o] = rv[k] > 0.f ? v : 0.f;
+        }
+    }
+    __shared__ float sg[8][D], sb[8][D];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { sg[warp][lane + 32 * k] = ag[k]; sb[warp][lane + 32 * k] = ab[k]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int w = 0; w < 8; ++w) { s1 += sg[w][c]; s2 += sb[w][c]; }
+        atomicAdd(ggamma + c, s1); atomicAdd(gbeta + c, s2);
+    }
+}
+
+// ---- attention backward, one CTA per (sequence, head); softmax probabilities are recomputed ----------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ d_o,
+                float* __restrict__ d_qkv, int L, int d, float scale) {
+    __shared__ float Qs[128][HD + 1], Ks[128][HD + 1], Vs[128][HD + 1], Gs[128][HD + 1];
+    __shared__ float sm_m[128], sm_il[128], sm_D[128];
+    const int h = blockIdx.x;
+    const size_t t0 = (size_t)blockIdx.y * L;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < L * (HD / 4); e += blockDim.x) {
+        const int r = e / (HD / 4), c4 = (e % (HD / 4)) * 4;
+        const float* base = qkv + (t0 + r) * (size_t)(3 * d) + h * HD + c4;
+        const float4 qv = *reinterpret_cast<const float4*>(base);
+        const float4 kv = *reinterpret_cast<const float4*>(base + d);
+        const float4 vv = *reinterpret_cast<const float4*>(base + 2 * d);
+        const float4 gv = *reinterpret_cast<const float4*>(d_o + (t0 + r) * (size_t)d + h * HD + c4);
+        Qs[r][c4] = qv.x * scale; Qs[r][c4 + 1] = qv.y * scale; Qs[r][c4 + 2] = qv.z * scale; Qs[r][c4 + 3] = qv.w * scale;
+        Ks[r][c4] = kv.x; Ks[r][c4 + 1] = kv.y; Ks[r][c4 + 2] = kv.z; Ks[r][c4 + 3] = kv.w;
+        Vs[r][c4] = vv.x; Vs[r][c4 + 1] = vv.y; Vs[r][c4 + 2] = vv.z; Vs[r][c4 + 3] = vv.w;
+        Gs[r][c4] = gv.x; Gs[r][c4 + 1] = gv.y; Gs[r][c4 + 2] = gv.z; Gs[r][c4 + 3] = gv.w;
+    }
+    __syncthreads();
+    const int j = tid;
+    // phase A (thread = query row j): softmax statistics, D_j = dO_j . O_j, dQ_j
+    if (j < L) {
+        float q[HD], g[HD];
+#pragma unroll
+        for (int c = 0; c < HD; ++c) { q[c] = Qs[j][c]; g[c] = Gs[j][c]; }
+        float m = -INFINITY;
+        for (int i = 0; i <= j; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) s = fmaf(q[c], Ks[i][c], s);
+            m = fmaxf(m, s);
+        }
+        float l = 0.f;
+        for (int i = 0; i <= j; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) s = fmaf(q[c], Ks[i][c], s);
+            l += expf(s - m);
+        }
+        const float il = 1.f / l;
+        float D = 0.f;
+        const float* op = o + (t0 + j) * (size_t)d + h * HD;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) D = fmaf(g[c], op[c], D);
+        float dq[HD];
+#pragma unroll
+        for (int c = 0; c < HD; ++c) dq[c] = 0.f;
+        for (int i = 0; i <= j; ++i) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { s = fmaf(q[c], Ks[i][c], s); dp = fmaf(g[c], Vs[i][c], dp); }
+            const float p = expf(s - m) * il;
+            const float ds = p * (dp - D);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) dq[c] = fmaf(ds, Ks[i][c], dq[c]);
+        }
+        sm_m[j] = m; sm_il[j] = il; sm_D[j] = D;
+        float* dst = d_qkv + (t0 + j) * (size_t)(3 * d) + h * HD;
+#pragma unroll
+        for (int c4 = 0; c4 < HD; c4 += 4)
+            *reinterpret_cast<float4*>(dst + c4) = make_float4(dq[c4] * scale, dq[c4 + 1] * scale, dq[c4 + 2] * scale, dq[c4 + 3] * scale);
+    }
+    __syncthreads();
+    // phase B (thread = key row i): dK_i = sum_{j>=i} ds_ji (q_j * scale), dV_i = sum_{j>=i} p_ji dO_j
+    const int i = tid;
+    if (i < L) {
+        float k[HD], v[HD], dk[HD], dv[HD];
+#pragma unroll
+        for (int c = 0; c < HD; ++c) { k[c] = Ks[i][c]; v[c] = Vs[i][c]; dk[c] = 0.f; dv[c] = 0.f; }
+        for (int jj = i; jj < L; ++jj) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { s = fmaf(Qs[jj][c], k[c], s); dp = fmaf(Gs[jj][c], v[c], dp); }
+            const float p = expf(s - sm_m[jj]) * sm_il[jj];
+            const float ds = p * (dp - sm_D[jj]);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { dk[c] = fmaf(ds, Qs[jj][c], dk[c]); dv[c] = fmaf(p, Gs[jj][c], dv[c]); }
+        }
+        float* dst = d_qkv + (t0 + i) * (size_t)(3 * d) + h * HD;
+#pragma unroll
+        for (int c4 = 0; c4 < HD; c4 += 4) {
+            *reinterpret_cast<float4*>(dst + d + c4) = make_float4(dk[c4], dk[c4 + 1], dk[c4 + 2], dk[c4 + 3]);
+            *reinterpret_cast<float4*>(dst + 2 * d + c4) = make_float4(dv[c4], dv[c4 + 1], dv[c4 + 2], dv[c4 + 3]);
+        }
+    }
+}
+
+// ---- embedding backward ------------------------------------------------------------------------------------------------------------
+// position table: gpos[j, c] = sum_b dx0[b, j, c]   (one thread per (j, c), no atomics)
+__global__ void pos_bwd_kernel(const float* __restrict__ dx0, int B, int L, int d, float* __restrict__ gpos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L * d) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dx0[(size_t)b * L * d + idx];
+    gpos[idx] = s;
+}
+
+// obs embedding: continuous  gW[c,k] += sum_t dx0[t,c] obs[t,k];  discrete: through Embedding->Flatten->Linear.
+// 32 tokens per CTA.
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c, const float* __restrict__ params,
+                 long long emb_table, long long emb_w, int L, int T, float* __restrict__ g_table,
+                 float* __restrict__ g_w, float* __restrict__ g_b) {
+    extern __shared__ float smem[];
+    const int d = c.d_model, O = c.obs_dim, E = c.discrete ? c.embed_per_obs : 1, KI = O * E;
+    float* sdx = smem;                 // [32][d]
+    float* sin_ = smem + 32 * d;       // [32][KI]  input features of the Linear (obs or looked-up embeddings)
+    int* stok = reinterpret_cast<int*>(sin_ + 32 * KI);   // [32][O] token ids (discrete)
+    const int t0 = blockIdx.x * 32, nt = min(32, T - t0);
+    for (int e = threadIdx.x; e < 32 * d; e += blockDim.x) {
+        const int r = e / d;
+        sdx[e] = r < nt ? dx0[(size_t)(t0 + r) * d + (e % d)] : 0.f;
+    }
+    for (int e = threadIdx.x; e < 32 * O; e += blockDim.x) {
+        const int r = e / O, k = e % O;
+        float ov = 0.f;
+        if (r < nt) {
+            const int t = t0 + r, i = t / L, j = t % L;
+            ov = src.obs[(long long)i * src.seq_stride + (long long)j * O + k];
+        }
+        if (c.discrete) {
+            int tok = (int)ov; tok = tok < 0 ? 0 : (tok >= c.vocab ? c.vocab - 1 : tok);
+            stok[e] = tok;
+            for (int ee = 0; ee < E; ++ee) sin_[r * KI + k * E + ee] = r < nt ? params[emb_table + tok * E + ee] : 0.f;
+        } else sin_[r * KI + k] = ov;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < d * KI; e += blockDim.x) {          // gW[c, f] += sum_r dx[r, c] * in[r, f]
+        const int cc = e / KI, f = e % KI;
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s = fmaf(sdx[r * d + cc], sin_[r * KI + f], s);
+        atomicAdd(g_w + e, s);
+    }
+    for (int cc = threadIdx.x; cc < d; cc += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s += sdx[r * d + cc];
+        atomicAdd(g_b + cc, s);
+    }
+    if (c.discrete) {
+        for (int e = threadIdx.x; e < nt * KI; e += blockDim.x) {     // d table[tok(r,k), ee] += sum_c dx[r,c] W[c, f]
+            const int r = e / KI, f = e % KI;
+            float s = 0.f;
+            for (int cc = 0; cc < d; ++cc) s = fmaf(sdx[r * d + cc], __ldg(params + emb_w + (long long)cc * KI + f), s);
+            atomicAdd(g_table + stok[r * O + f / E] * E + (f % E), s);
+        }
+    }
+}
+
+template <int EPI>
+int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
+    dim3 grid(dtqn_cdiv(T, GEMM_BM), 1, 1);
+    if (Kf % 128 == 0) { grid.y = Kf / 128; dgrad_kernel<128, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
+    else if (Kf % 64 == 0) { grid.y = Kf / 64; dgrad_kernel<64, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
+    else return DTQN_E_UNSUPPORTED;
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gW, float* gb, cudaStream_t st) {
+    if (Nf % 64 || Kf % 64) return DTQN_E_UNSUPPORTED;
+    dim3 grid(Nf / 64, Kf / 64, dtqn_cdiv(T, WG_CHUNK));
+    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gW, gb);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+struct BwdScratch {
+    float *dq, *g_hh, *gx, *gu, *ga, *gh, *gqkv, *go, *gx1, *partial;
+    unsigned* ticket;
+    long long total;
+};
+long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, BwdScratch& s) {
+    const long long d = c.d_model;
+    long long o = 0;
+    auto take = [&](long long n) { float* p = base ? base + o : nullptr; o = al4(o + n); return p; };
+    s.dq = take(T0 * c.num_actions); s.g_hh = take(T0 * d); s.gx = take(T0 * d); s.gu = take(T0 * d);
+    s.ga = take(T0 * d); s.gh = take(T0 * 4 * d); s.gqkv = take(T0 * 3 * d); s.go = take(T0 * d); s.gx1 = take(T0 * d);
+    s.partial = take((long long)dtqn_cdiv(T0, 256) * 8);
+    s.ticket = reinterpret_cast<unsigned*>(take(4));
+    s.total = o;
+    return o;
+}
+
+}  // namespace
+
+extern "C" int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len) {
+    if (!cfg || batch < 1 || seq_len < 1) return DTQN_E_ARG;
+    BwdScratch s;
+    return bwd_scratch_layout(*cfg, (long long)batch * seq_len, nullptr, s);
+}
+
+extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, const dtqn_obs_src* obs_src,
+                                const float* q_all, const uint8_t* act_win, const float* rew, const uint8_t* done,
+                                int32_t B, int32_t L, int32_t history, float gamma, float* ws, int64_t ws_floats,
+                                float* scratch, float* grads, float* stats_out, void* stream) {
+    if (!cfg || !params || !obs_src || !obs_src->obs || obs_src->timestep || !q_all || !act_win || !rew || !done ||
+        !ws || !scratch || !grads || !stats_out || B < 1 || L < 1 || history < 1 || history > L) return DTQN_E_ARG;
+    NetLayout lay;
+    int rc = net_layout(*cfg, lay);
+    if (rc) return rc;
+    const long long T0 = (long long)B * L, T = 3 * T0;
+    NetAct act;
+    if (net_act_layout(*cfg, T, 1, ws, act) > ws_floats) return DTQN_E_ARG;
+    BwdScratch s;
+    bwd_scratch_layout(*cfg, T0, scratch, s);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = cfg->d_model, H = cfg->n_heads, hd = d / H, A = cfg->num_actions, Ti = (int)T0;
+    cudaError_t ce = cudaMemsetAsync(grads, 0, sizeof(float) * lay.total, st);
+    if (ce != cudaSuccess) return (int)ce;
+
+    td_loss_kernel<<<dtqn_cdiv(T0, 256), 256, 0, st>>>(q_all, act_win, rew, done, B, L, A, history, gamma, s.dq,
+                                                        s.partial, s.ticket, stats_out);
+    DTQN_LAUNCH_CHECK();
+    // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
+    head_bwd_kernel<<<dtqn_cdiv(T0, 64), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
+                                                        grads + lay.h2_w, grads + lay.h2_b);
+    DTQN_LAUNCH_CHECK();
+    const float* x_last = act.layer[cfg->n_layers - 1].x2;
+    if ((rc = launch_wgrad(s.g_hh, x_last, Ti, d, d, grads + lay.h1_w, grads + lay.h1_b, st))) return rc;
+    if ((rc = launch_dgrad<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, s.gx, Ti, d, d, st))) return rc;
+    for (int li = cfg->n_layers - 1; li >= 0; --li) {
+        const LayerOff& lo = lay.layer[li];
+        const LayerAct& la = act.layer[li];
+        const float* x_in = li == 0 ? act.x0 : act.layer[li - 1].x2;
+        // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
+        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
+        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
+        DTQN_LAUNCH_CHECK();
+        // ffn.2
+        if ((rc = launch_wgrad(s.ga, la.h, Ti, d, 4 * d, grads + lo.f2_w, grads + lo.f2_b, st))) return rc;
+        if ((rc = launch_dgrad<DG_MASK>(s.ga, params + lo.f2_w, la.h, s.gh, Ti, d, 4 * d, st))) return rc;
+        // ffn.0
+        if ((rc = launch_wgrad(s.gh, la.x1, Ti, 4 * d, d, grads + lo.f1_w, grads + lo.f1_b, st))) return rc;
+        if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
+        // LN1 backward: dy = gx1 -> gu (du1), ga (d out_proj output)
+        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
+        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
+        DTQN_LAUNCH_CHECK();
+        // out_proj
+        if ((rc = launch_wgrad(s.ga, la.o, Ti, d, d, grads + lo.out_w, grads + lo.out_b, st))) return rc;
+        if ((rc = launch_dgrad<DG_NONE>(s.ga, params + lo.out_w, nullptr, s.go, Ti, d, d, st))) return rc;
+        // attention core
+        {
+            dim3 grid(H, (unsigned)B);
+            const int thr = L <= 64 ? 64 : 128;
+            const float scale = 1.0f / sqrtf((float)hd);
+            if (hd == 8) attn_bwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            else if (hd == 16) attn_bwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            else if (hd == 4) attn_bwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            else return DTQN_E_UNSUPPORTED;
+            DTQN_LAUNCH_CHECK();
+        }
+        // in_proj
+        if ((rc = launch_wgrad(s.gqkv, x_in, Ti, 3 * d, d, grads + lo.in_w, grads + lo.in_b, st))) return rc;
+        if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
+    }
+    // embedding + position table
+    if (cfg->pos_trainable) {
+        pos_bwd_kernel<<<dtqn_cdiv((long long)L * d, 256), 256, 0, st>>>(s.gx, B, L, d, grads + lay.pos);
+        DTQN_LAUNCH_CHECK();
+    }
+    {
+        const int KI = lay.k_in;
+        const size_t smem = sizeof(float) * (32 * d + 32 * KI) + sizeof(int) * 32 * cfg->obs_dim;
+        embed_bwd_kernel<<<dtqn_cdiv(T0, 32), 256, smem, st>>>(s.gx, *obs_src, *cfg, params, lay.emb_table, lay.emb_w, L, Ti,
+                                                              cfg->discrete ? grads + lay.emb_table : nullptr,
+                                                              grads + lay.emb_w, grads + lay.emb_b);
+        DTQN_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -1,0 +1,385 @@
+// DTQN Q-network forward (dtqn/networks/dtqn.py:158-218) as sm_100a kernels.
+//   embed_kernel      obs embedding (Linear(O,d) or Embedding->Flatten->Linear, representations.py:17-75) + position
+//                     table add (dtqn.py:195-199); reads a dense batch, the replay window or the acting-context ring
+//   linear_kernel     x W^T + b with fused epilogues: bias | bias+ReLU | bias -> ReLU -> +residual -> LayerNorm
+//                     (transformer.py:64-78: x = LN(x + relu(sublayer(x))), gates.py:40-41)
+//   attn_fwd_kernel   causal multi-head self-attention core (softmax((q/sqrt(hd)) k^T + mask) v), one CTA per
+//                     (sequence, head), online softmax in registers (nn.MultiheadAttention closed form)
+//   head_kernel       final Linear(d, A) (dtqn.py:149-153), one warp per token
+#include "net.cuh"
+#include "gemm_simt.cuh"
+
+namespace {
+
+struct GroupPtrs { const float* p[DTQN_MAX_GROUPS]; };
+struct GroupSrc { dtqn_obs_src s[DTQN_MAX_GROUPS]; };
+
+// ---- observation embedding + position ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_kernel(GroupPtrs P, GroupSrc S, dtqn_net_cfg c, long long emb_table, long long emb_w, long long emb_b,
+             long long pos_off, int n_seq, int L, float obs_mask, float* __restrict__ x0) {
+    const int g = blockIdx.z;
+    const int d = c.d_model, dq = d / 4;
+    const long long Tg = (long long)n_seq * L;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Tg * dq) return;
+    const long long t = idx / dq;
+    const int c0 = (int)(idx % dq) * 4;
+    const int i = (int)(t / L), j = (int)(t % L);
+    const dtqn_obs_src& s = S.s[g];
+    int row = j;
+    bool valid = true;
+    if (s.timestep) {
+        const int ts = s.timestep[i];
+        const int n = min(s.ring_len, ts + 1);
+        valid = j < n;
+        row = valid ? (ts + 1 - n + j) % s.ring_len : 0;
+    }
+    const float* o = s.obs + (long long)i * s.seq_stride + (long long)row * c.obs_dim;
+    const float* p = P.p[g];
+    float acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = __ldg(p + emb_b + c0 + q);
+    if (!c.discrete) {
+        const int O = c.obs_dim;
+        for (int k = 0; k < O; ++k) {
+            const float ov = valid ? __ldg(o + k) : obs_mask;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(ov, __ldg(p + emb_w + (long long)(c0 + q) * O + k), acc[q]);
+        }
+    } else {
+        const int O = c.obs_dim, E = c.embed_per_obs, KI = O * E;
+        for (int k = 0; k < O; ++k) {
+            const float ov = valid ? __ldg(o + k) : obs_mask;
+            int tok = (int)ov;
+            tok = tok < 0 ? 0 : (tok >= c.vocab ? c.vocab - 1 : tok);
+            for (int e = 0; e < E; ++e) {
+                const float tv = __ldg(p + emb_table + tok * E + e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    acc[q] = fmaf(tv, __ldg(p + emb_w + (long long)(c0 + q) * KI + k * E + e), acc[q]);
+            }
+        }
+    }
+    const float4 pv = *reinterpret_cast<const float4*>(p + pos_off + (long long)j * d + c0);
+    float4 out = make_float4(acc[0] + pv.x, acc[1] + pv.y, acc[2] + pv.z, acc[3] + pv.w);
+    *reinterpret_cast<float4*>(x0 + ((long long)g * Tg + t) * d + c0) = out;
+}
+
+// ---- Linear with fused epilogues --------------------------------------------------------------------------------------
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_RES_LN = 2 };
+
+struct LinArgs {
+    const float* X;        // [G*Tg, K]
+    float* Y;              // [G*Tg, N]
+    GroupPtrs P;
+    long long w_off, b_off;
+    int Tg, N, K;
+    // EPI_RES_LN only (N == BN == d_model):
+    const float* R;        // residual input [G*Tg, N]
+    long long gamma_off, beta_off;
+    float* r_save;         // relu(a) [G*Tg, N]   (nullable)
+    float* st_save;        // (mean, rstd) [G*Tg, 2] (nullable)
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS)
+linear_kernel(LinArgs a) {
+    __shared__ GemmSmem<BN> sm;
+    constexpr int TN = BN / 16;
+    const int g = blockIdx.z;
+    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+    const float* p = a.P.p[g];
+    const size_t grow = (size_t)g * a.Tg;
+    float acc[4][TN];
+    gemm_tile_64<BN, false>(a.X + grow * a.K, a.K, a.Tg, p + a.w_off, a.K, a.K, m0, n0, acc, sm);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float bias[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bias[j] = __ldg(p + a.b_off + n0 + gemm_col(tx, j));
+    if (EPI != EPI_RES_LN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + ty * 4 + i;
+            if (r >= a.Tg) continue;
+            float* y = a.Y + (grow + r) * a.N + n0;
+#pragma unroll
+            for (int j4 = 0; j4 < TN / 4; ++j4) {
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q] = acc[i][j4 * 4 + q] + bias[j4 * 4 + q];
+                    if (EPI == EPI_BIAS_RELU) v[q] = fmaxf(v[q], 0.f);
+                }
+                *reinterpret_cast<float4*>(y + j4 * 64 + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    } else {
+        // x_out = LayerNorm(x_res + relu(acc + b)) over the full row (BN == N); the 16 lanes of a half-warp share a row
+        float gam[TN], bet[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            gam[j] = __ldg(p + a.gamma_off + gemm_col(tx, j));
+            bet[j] = __ldg(p + a.beta_off + gemm_col(tx, j));
+        }
+        const float inv_n = 1.f / (float)BN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + ty * 4 + i;
+            const bool ok = r < a.Tg;                         // all 16 lanes of the row agree
+            const size_t ro = (grow + (ok ? r : 0)) * (size_t)BN;
+            float u[TN], rl[TN];
+            float s = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < TN / 4; ++j4) {
+                const float4 xr = *reinterpret_cast<const float4*>(a.R + ro + j4 * 64 + tx * 4);
+                const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j4 * 4 + q;
+                    rl[j] = fmaxf(acc[i][j] + bias[j], 0.f);
+                    u[j] = xv[q] + rl[j];
+                    s += u[j];
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * inv_n;
+            float vs = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { const float dlt = u[j] - mean; vs = fmaf(dlt, dlt, vs); }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+            const float rstd = 1.0f / sqrtf(vs * inv_n + 1e-5f);
+            if (!ok) continue;
+#pragma unroll
+            for (int j4 = 0; j4 < TN / 4; ++j4) {
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int j = j4 * 4 + q; v[q] = (u[j] - mean) * rstd * gam[j] + bet[j]; }
+                *reinterpret_cast<float4*>(a.Y + ro + j4 * 64 + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                if (a.r_save)
+                    *reinterpret_cast<float4*>(a.r_save + ro + j4 * 64 + tx * 4) =
+                        make_float4(rl[j4 * 4], rl[j4 * 4 + 1], rl[j4 * 4 + 2], rl[j4 * 4 + 3]);
+            }
+            if (a.st_save && tx == 0) { a.st_save[(grow + r) * 2] = mean; a.st_save[(grow + r) * 2 + 1] = rstd; }
+        }
+    }
+}
+
+// ---- causal self-attention core ------------------------------------------------------------------------------------------
+// qkv [T, 3d]: q at column h*hd, k at d + h*hd, v at 2d + h*hd (packed in_proj layout).  o [T, d].
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int d, float scale) {
+    __shared__ float Ks[128][HD + 1];
+    __shared__ float Vs[128][HD + 1];
+    const int h = blockIdx.x;
+    const size_t t0 = (size_t)blockIdx.y * L;
+    const int tid = threadIdx.x;
+    // cooperative load of K and V head slices: L rows x HD floats each
+    for (int e = tid; e < L * (HD / 4); e += blockDim.x) {
+        const int r = e / (HD / 4), c4 = (e % (HD / 4)) * 4;
+        const float* base = qkv + (t0 + r) * (size_t)(3 * d) + h * HD + c4;
+        const float4 kv = *reinterpret_cast<const float4*>(base + d);
+        const float4 vv = *reinterpret_cast<const float4*>(base + 2 * d);
+        Ks[r][c4] = kv.x; Ks[r][c4 + 1] = kv.y; Ks[r][c4 + 2] = kv.z; Ks[r][c4 + 3] = kv.w;
+        Vs[r][c4] = vv.x; Vs[r][c4 + 1] = vv.y; Vs[r][c4 + 2] = vv.z; Vs[r][c4 + 3] = vv.w;
+    }
+    __syncthreads();
+    const int j = tid;
+    if (j >= L) return;
+    float q[HD], accv[HD];
+    const float* qp = qkv + (t0 + j) * (size_t)(3 * d) + h * HD;
+#pragma unroll
+    for (int c4 = 0; c4 < HD; c4 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(qp + c4);
+        q[c4] = v.x * scale; q[c4 + 1] = v.y * scale; q[c4 + 2] = v.z * scale; q[c4 + 3] = v.w * scale;
+    }
+#pragma unroll
+    for (int c = 0; c < HD; ++c) accv[c] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i <= j; ++i) {                           // causal: keys 0..j (mask is -inf above the diagonal)
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) s = fmaf(q[c], Ks[i][c], s);
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn);                     // exp(-inf) = 0 on the first key
+        const float pw = expf(s - mn);
+        l = l * corr + pw;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) accv[c] = fmaf(pw, Vs[i][c], accv[c] * corr);
+        m = mn;
+    }
+    const float inv = 1.f / l;
+    float* op = o + (t0 + j) * (size_t)d + h * HD;
+#pragma unroll
+    for (int c4 = 0; c4 < HD; c4 += 4)
+        *reinterpret_cast<float4*>(op + c4) = make_float4(accv[c4] * inv, accv[c4 + 1] * inv, accv[c4 + 2] * inv, accv[c4 + 3] * inv);
+}
+
+// ---- rows of the last valid position of every sequence (acting: q[:, -1, :], agents/dtqn.py:107) ---------------------
+__global__ void gather_last_kernel(const float* __restrict__ x, GroupSrc S, int n_seq, int L, int d, float* __restrict__ out) {
+    const int g = blockIdx.z;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_seq * d) return;
+    const int i = (int)(idx / d), cch = (int)(idx % d);
+    int last = L - 1;
+    const dtqn_obs_src& s = S.s[g];
+    if (s.timestep) { const int n = min(min(s.ring_len, s.timestep[i] + 1), L); last = n - 1; }
+    out[((long long)g * n_seq + i) * d + cch] = x[(((long long)g * n_seq + i) * L + last) * d + cch];
+}
+
+// ---- final Linear(d, A): one warp per token --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ hh, GroupPtrs P, long long w_off, long long b_off, long long Tg, int d, int A,
+            float* __restrict__ q) {
+    const int g = blockIdx.z;
+    const long long t = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (t >= Tg) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = P.p[g];
+    const float* x = hh + ((long long)g * Tg + t) * d;
+    float xv[4];
+    const int per = d / 32;                                   // 2 (d = 64) or 4 (d = 128)
+    for (int k = 0; k < per; ++k) xv[k] = x[lane + 32 * k];
+    for (int a = 0; a < A; ++a) {
+        float s = 0.f;
+        for (int k = 0; k < per; ++k) s = fmaf(xv[k], __ldg(p + w_off + (long long)a * d + lane + 32 * k), s);
+        s = warp_sum(s);
+        if (lane == 0) q[((long long)g * Tg + t) * A + a] = s + __ldg(p + b_off + a);
+    }
+}
+
+template <int EPI>
+int launch_linear(const LinArgs& a, int G, int d_model, cudaStream_t st) {
+    dim3 grid(dtqn_cdiv(a.Tg, GEMM_BM), 1, G);
+    if (EPI == EPI_RES_LN) {
+        if (a.N == 64) linear_kernel<64, EPI_RES_LN><<<grid, GEMM_THREADS, 0, st>>>(a);
+        else if (a.N == 128) linear_kernel<128, EPI_RES_LN><<<grid, GEMM_THREADS, 0, st>>>(a);
+        else return DTQN_E_UNSUPPORTED;
+    } else {
+        if (a.N % 128 == 0) { grid.y = a.N / 128; linear_kernel<128, EPI><<<grid, GEMM_THREADS, 0, st>>>(a); }
+        else if (a.N % 64 == 0) { grid.y = a.N / 64; linear_kernel<64, EPI><<<grid, GEMM_THREADS, 0, st>>>(a); }
+        else return DTQN_E_UNSUPPORTED;
+    }
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// ---- exported --------------------------------------------------------------------------------------------------------------
+extern "C" int64_t dtqn_net_param_count(const dtqn_net_cfg* cfg) {
+    if (!cfg) return DTQN_E_ARG;
+    NetLayout L;
+    int rc = net_layout(*cfg, L);
+    return rc ? rc : L.total;
+}
+
+extern "C" int dtqn_net_param_offsets(const dtqn_net_cfg* cfg, int64_t* out, int32_t max_entries) {
+    if (!cfg || !out) return DTQN_E_ARG;
+    NetLayout L;
+    int rc = net_layout(*cfg, L);
+    if (rc) return rc;
+    int n = 0;
+    auto put = [&](long long v) { if (n < max_entries) out[n] = v; ++n; };
+    if (cfg->discrete) put(L.emb_table);
+    put(L.emb_w); put(L.emb_b); put(L.pos);
+    for (int i = 0; i < cfg->n_layers; ++i) {
+        const LayerOff& l = L.layer[i];
+        put(l.ln1_w); put(l.ln1_b); put(l.ln2_w); put(l.ln2_b); put(l.in_w); put(l.in_b); put(l.out_w); put(l.out_b);
+        put(l.f1_w); put(l.f1_b); put(l.f2_w); put(l.f2_b);
+    }
+    put(L.h1_w); put(L.h1_b); put(L.h2_w); put(L.h2_b);
+    return n > max_entries ? DTQN_E_ARG : n;
+}
+
+extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_tokens, int32_t save) {
+    if (!cfg || n_tokens <= 0) return DTQN_E_ARG;
+    NetAct A;
+    return net_act_layout(*cfg, n_tokens, save, nullptr, A);
+}
+
+extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const dtqn_obs_src* src,
+                            int32_t n_seq, int32_t L, int32_t q_mode, int32_t save, float* ws, int64_t ws_floats,
+                            float* q_out, void* stream) {
+    if (!cfg || !params || !src || !ws || !q_out || G < 1 || G > DTQN_MAX_GROUPS || n_seq < 1 || L < 1) return DTQN_E_ARG;
+    if (L > cfg->context_len) return DTQN_E_ARG;               // dtqn.py:171-173 assert
+    NetLayout lay;
+    int rc = net_layout(*cfg, lay);
+    if (rc) return rc;
+    const long long Tg = (long long)n_seq * L, T = Tg * G;
+    NetAct act;
+    if (net_act_layout(*cfg, T, save, ws, act) > ws_floats) return DTQN_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = cfg->d_model, H = cfg->n_heads, hd = d / H;
+    GroupPtrs P{}; GroupSrc S{};
+    for (int g = 0; g < G; ++g) {
+        if (!params[g] || !src[g].obs) return DTQN_E_ARG;
+        P.p[g] = params[g]; S.s[g] = src[g];
+        if (src[g].timestep && src[g].ring_len < L) return DTQN_E_ARG;
+    }
+    {
+        dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
+        embed_kernel<<<grid, 256, 0, st>>>(P, S, *cfg, lay.emb_table, lay.emb_w, lay.emb_b, lay.pos, n_seq, L,
+                                            cfg->discrete ? (float)(cfg->vocab - 1) : -5.0f, act.x0);
+        DTQN_LAUNCH_CHECK();
+    }
+    const float* x_in = act.x0;
+    for (int li = 0; li < cfg->n_layers; ++li) {
+        const LayerOff& lo = lay.layer[li];
+        const LayerAct& la = act.layer[li];
+        LinArgs a{};
+        a.P = P; a.Tg = (int)Tg;
+        // in_proj
+        a.X = x_in; a.Y = la.qkv; a.w_off = lo.in_w; a.b_off = lo.in_b; a.N = 3 * d; a.K = d;
+        if ((rc = launch_linear<EPI_BIAS>(a, G, d, st))) return rc;
+        // attention core
+        {
+            dim3 grid(H, (unsigned)(n_seq * G));
+            const int thr = L <= 64 ? 64 : 128;
+            const float scale = 1.0f / sqrtf((float)hd);
+            if (hd == 8) attn_fwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+            else if (hd == 16) attn_fwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+            else if (hd == 32) attn_fwd_kernel<32><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+            else if (hd == 4) attn_fwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+            else return DTQN_E_UNSUPPORTED;
+            DTQN_LAUNCH_CHECK();
+        }
+        // out_proj -> relu -> +x -> LN1
+        a.X = la.o; a.Y = la.x1; a.w_off = lo.out_w; a.b_off = lo.out_b; a.N = d; a.K = d;
+        a.R = x_in; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b;
+        a.r_save = save ? la.r1 : nullptr; a.st_save = save ? la.st1 : nullptr;
+        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        // ffn.0 + relu
+        a.X = la.x1; a.Y = la.h; a.w_off = lo.f1_w; a.b_off = lo.f1_b; a.N = 4 * d; a.K = d;
+        if ((rc = launch_linear<EPI_BIAS_RELU>(a, G, d, st))) return rc;
+        // ffn.2 -> relu -> +x1 -> LN2
+        a.X = la.h; a.Y = la.x2; a.w_off = lo.f2_w; a.b_off = lo.f2_b; a.N = d; a.K = 4 * d;
+        a.R = la.x1; a.gamma_off = lo.ln2_w; a.beta_off = lo.ln2_b;
+        a.r_save = save ? la.r2 : nullptr; a.st_save = save ? la.st2 : nullptr;
+        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        x_in = la.x2;
+    }
+    // Q head
+    long long Th = Tg;
+    const float* head_in = x_in;
+    if (q_mode == 1) {
+        // only the last valid position feeds the head; qkv of layer 0 is free scratch by now
+        float* xl = act.layer[0].qkv;
+        dim3 grid(dtqn_cdiv((long long)n_seq * d, 256), 1, G);
+        gather_last_kernel<<<grid, 256, 0, st>>>(x_in, S, n_seq, L, d, xl);
+        DTQN_LAUNCH_CHECK();
+        head_in = xl; Th = n_seq;
+    }
+    {
+        LinArgs a{};
+        a.P = P; a.Tg = (int)Th; a.X = head_in; a.Y = act.hh; a.w_off = lay.h1_w; a.b_off = lay.h1_b; a.N = d; a.K = d;
+        if ((rc = launch_linear<EPI_BIAS_RELU>(a, G, d, st))) return rc;
+        dim3 grid(dtqn_cdiv(Th, 8), 1, G);
+        head_kernel<<<grid, 256, 0, st>>>(act.hh, P, lay.h2_w, lay.h2_b, Th, d, cfg->num_actions, q_out);
+        DTQN_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -148,6 +148,11 @@ class ContextWindow:
                                          trunc_obs=int(self.trunc_obs), obs_mask=self.obs_mask,
                                          obs=_lib.ptr(self.obs), timestep=_lib.ptr(self.timestep_t))
 
+    @property
+    def timestep(self) -> int:
+        """Context.timestep of env 0 (run.py:231 reads it after an evaluation episode)."""
+        return int(self.timestep_t[0].item())
+
     def windows(self):
         """Dense [n, ctx, O] windows in temporal order + valid lengths [n] (host-side helper for tests)."""
         t = self.timestep_t.long()

@@ -131,6 +131,74 @@ int dtqn_replay_sample_indices(const dtqn_replay* rb, int32_t batch, uint64_t se
 int dtqn_replay_gather(const dtqn_replay* rb, int32_t batch, const int32_t* episodes, const int32_t* starts,
                        float* obs_win, uint8_t* act_win, float* rew, uint8_t* done, int32_t* eplen, void* stream);
 
+
+/* ==== DTQN Q-network: dtqn/networks/dtqn.py:15-218, transformer.py:6-78, representations.py:9-75,146-155,
+ *      position_encodings.py:14-51, gates.py:34-41 (ResGate) ==================================================== */
+typedef struct dtqn_net_cfg {
+    int32_t obs_dim;        /* O: length of the observation vector */
+    int32_t num_actions;    /* A */
+    int32_t d_model;        /* inner_embed_size (64 | 128) */
+    int32_t n_heads;
+    int32_t n_layers;
+    int32_t context_len;    /* history_len: rows of the position table, max sequence length */
+    int32_t discrete;       /* 0: Linear(O, d) on float obs; 1: Embedding(vocab, e) -> Flatten -> Linear(O*e, d) */
+    int32_t vocab;          /* discrete only: obs_mask + 1 (utils/agent_utils.py:92-95) */
+    int32_t embed_per_obs;  /* discrete only: e */
+    int32_t pos_trainable;  /* 1 = learned position table (gets a gradient), 0 = sin / none (still added) */
+} dtqn_net_cfg;
+
+/* Where a group of sequences reads its observations.  Sequence i, token j reads row
+ *   obs + i * seq_stride + j * obs_dim                                   (timestep == NULL), or, for the acting
+ * context ring (utils/context.py), row ((t_i + 1 - n_i + j) mod ring_len) with n_i = min(ring_len, t_i + 1). */
+typedef struct dtqn_obs_src {
+    const float*   obs;
+    int64_t        seq_stride;   /* floats */
+    const int32_t* timestep;     /* nullable */
+    int32_t        ring_len;
+    int32_t        _pad;
+} dtqn_obs_src;
+
+/* Number of floats of the flat parameter buffer, and the offset of every tensor in it, in this fixed order:
+ *   [emb_table (discrete only)], emb_w, emb_b, pos, then per layer: ln1_w, ln1_b, ln2_w, ln2_b, in_w, in_b, out_w,
+ *   out_b, f1_w, f1_b, f2_w, f2_b, then h1_w, h1_b, h2_w, h2_b.   Returns the tensor count (or < 0). */
+int64_t dtqn_net_param_count(const dtqn_net_cfg* cfg);
+int dtqn_net_param_offsets(const dtqn_net_cfg* cfg, int64_t* offsets_out, int32_t max_entries);
+/* Floats of activation workspace for n_tokens = groups * n_seq * seq_len tokens. */
+int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_tokens, int32_t save);
+
+/* DTQN.forward (dtqn.py:158-218) for n_groups <= 3 groups of n_seq sequences of seq_len tokens, group g using the
+ * flat parameter buffer params[g] and observation source src[g].
+ *   q_mode 0: q_out[g, i, j, :] for every position (training, dtqn/agents/dtqn.py:215-233);
+ *   q_mode 1: q_out[g, i, :] = Q at the last valid position n_i - 1 (acting, dtqn/agents/dtqn.py:101-107).
+ * save = 1 keeps every layer's activations in `workspace` for dtqn_td_backward. */
+int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* params, const dtqn_obs_src* src,
+                 int32_t n_seq, int32_t seq_len, int32_t q_mode, int32_t save, float* workspace,
+                 int64_t workspace_floats, float* q_out, void* stream);
+
+/* Double-DQN sequence TD loss + backward (dtqn/agents/dtqn.py:215-256) for a forward made with n_groups = 3,
+ * save = 1, q_mode = 0 over (policy|obs, policy|next_obs, target|next_obs).  Zeroes `grads` (flat, same layout as
+ * the parameters) and accumulates dLoss/dparam of group 0 into it.
+ *   act_win [B, L+1] u8 (actions = columns [0, L)), rew [B, L] f32, done [B, L] u8;
+ *   stats_out[8] = loss, q_max, q_mean, q_min, target_max, target_mean, target_min, (grad_norm: dtqn_clip_adam). */
+int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* policy_params, const dtqn_obs_src* obs_src,
+                     const float* q_all /* [3, B, L, A] */, const uint8_t* act_win, const float* rew, const uint8_t* done,
+                     int32_t batch, int32_t seq_len, int32_t history, float gamma, float* workspace,
+                     int64_t workspace_floats, float* scratch /* >= dtqn_td_scratch_floats */, float* grads,
+                     float* stats_out, void* stream);
+int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len);
+
+/* clip_grad_norm_(params, max_norm, error_if_nonfinite=True) + Adam.step (dtqn/agents/dtqn.py:257-265,
+ * dtqn/agents/dqn.py:64): grads *= grad_scale (1/world after the allreduce), total = ||grads||_2,
+ * coef = min(1, max_norm / (total + 1e-6)), Adam with bias correction at step *step_counter + 1 (incremented).
+ * stats_out[7] = total norm; flags_out[0] = 1 if the norm is non-finite (parameters untouched in that case).
+ * The 8 logged statistics of the step (the reference's RunningAverage.add(...item()) calls, agents/dtqn.py:245-263)
+ * are appended to a device ring instead of being synchronised to the host every step. */
+int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                   float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_counter,
+                   float* scratch /* >= 1024 floats */, float* stats_out, int32_t* flags_out,
+                   float* stats_ring /* nullable [ring_len, 8]: row (step-1) % ring_len <- stats_out[0..8) */,
+                   int32_t ring_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,131 @@
+"""GPU parity of the Q-network kernels: forward vs the reference's DTQN.forward outputs (golden), one-step and
+multi-step DtqnAgent.train parity (loss, statistics, raw gradients, post-Adam parameters), acting forward from the
+context ring.  Tolerance of record (BASELINE.json north_star): Q within 1e-3 rel fp32, rel = max|dQ| / max|Q_ref|."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+Q_REL_TOL = 1e-3          # north_star bar
+Q_REL_TIGHT = 2e-5        # what the fp32 CUDA-core path is expected to reach
+
+
+def _sd(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
+
+
+def _make_net(z, prefix, env):
+    from dtqn_b200.networks import DTQN
+    meta = [int(v) for v in z["meta"]]
+    d, layers, ctx, heads = meta[0], meta[1], meta[2], meta[3] if len(meta) == 4 else meta[4]
+    if env == "carflag":
+        net = DTQN(3, 3, 8, 0, d, heads, layers, ctx, pos="learned", discrete=False, device="cuda")
+    else:
+        net = DTQN(10, 10, 8, 0, d, heads, layers, ctx, pos="learned", discrete=True, vocab_sizes=9, device="cuda")
+    net.load_state_dict(_sd(z, prefix))
+    return net
+
+
+def rel_err(got, ref):
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12))
+
+
+@pytest.mark.parametrize("env", ["carflag", "memory"])
+def test_forward_matches_reference_q(golden_dir, env):
+    z = np.load(os.path.join(golden_dir, f"forward_{env}.npz"))
+    net = _make_net(z, "policy/", env)
+    assert sum(p.numel() for p in net.parameters()) == {"carflag": 112779, "memory": 436186}[env]
+    for L in (1, 7, int(z["meta"][2])):
+        x = torch.from_numpy(z[f"L{L}/obss"])
+        q = net(x).cpu().numpy()
+        ref = z[f"L{L}/q"]
+        e = rel_err(q, ref)
+        assert e < Q_REL_TOL and e < Q_REL_TIGHT, (L, e)
+
+
+def test_forward_asserts_like_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "forward_carflag.npz"))
+    net = _make_net(z, "policy/", "carflag")
+    with pytest.raises(AssertionError):
+        net(torch.zeros(2, 51, 3))           # dtqn.py:171-173
+    with pytest.raises(AssertionError):
+        net(torch.zeros(2, 5, 4))            # dtqn.py:177-179
+
+
+def _agent_from_golden(z, env, batch):
+    from dtqn_b200.agents import DtqnAgent
+    d, layers, ctx, B, heads, n_steps = [int(v) for v in z["meta"]]
+    mk = lambda: _make_net(z, "policy0/", env)
+    O, A, mask, E, disc = (3, 3, -5, 200, False) if env == "carflag" else (10, 10, 8, 50, True)
+    agent = DtqnAgent(mk, 50_000, "cuda", O, E, mask, A, disc, batch_size=B, context_len=ctx, history=ctx)
+    agent.target_network.load_state_dict(_sd(z, "target0/"))
+    return agent
+
+
+def _windows(z, s):
+    obs = np.concatenate([z[f"step{s}/obss"], z[f"step{s}/next_obss"][:, -1:]], axis=1).astype(np.float32)
+    act = np.concatenate([z[f"step{s}/actions"], z[f"step{s}/next_actions"][:, -1:]], axis=1)[..., 0].astype(np.uint8)
+    rew = z[f"step{s}/rewards"][..., 0].astype(np.float32)
+    done = z[f"step{s}/dones"][..., 0].astype(np.uint8)
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (obs, act, rew, done)]
+
+
+@pytest.mark.parametrize("env", ["carflag", "memory"])
+def test_train_steps_match_reference(golden_dir, env):
+    z = np.load(os.path.join(golden_dir, f"train_{env}.npz"))
+    d, layers, ctx, B, heads, n_steps = [int(v) for v in z["meta"]]
+    agent = _agent_from_golden(z, env, B)
+    agent.strict_finite = True
+    for s in range(n_steps):
+        agent.train_on_windows(*_windows(z, s))
+        st = agent.stats.cpu().numpy()
+        ref = [z["stats/td_errors"][s], z["stats/qvalue_max"][s], z["stats/qvalue_mean"][s], z["stats/qvalue_min"][s],
+               z["stats/target_max"][s], z["stats/target_mean"][s], z["stats/target_min"][s], z["stats/grad_norms"][s]]
+        for k, (g, r) in enumerate(zip(st, ref)):
+            assert abs(g - r) <= 1e-4 * max(1.0, abs(r)), (s, k, g, r)
+        if s == 0:
+            q_all = agent._q_all.cpu().numpy()
+            for gi, key in enumerate(("q_policy_obs", "q_policy_next", "q_target_next")):
+                assert rel_err(q_all[gi], z["step0/" + key]) < Q_REL_TIGHT, key
+            grads = agent.policy_network.unflatten(agent.grads)
+            gmax = max(np.abs(z["step0/grad/" + k]).max() for k in grads if ("step0/grad/" + k) in z.files)
+            for k, g in grads.items():
+                ref_g = z["step0/grad/" + k]
+                err = np.abs(g.cpu().numpy() - ref_g).max()
+                assert err <= 1e-3 * max(np.abs(ref_g).max(), 1e-3 * gmax), (k, err, np.abs(ref_g).max())
+    for k, p in agent.policy_network.state_dict().items():
+        ref_p = z[f"policy{n_steps}/" + k]
+        assert np.abs(p.cpu().numpy() - ref_p).max() < 2e-5, k
+    # stats ring == the reference's RunningAverage contents
+    assert abs(agent.td_errors.mean() - z["stats/td_errors"].mean()) < 1e-5
+    assert abs(agent.grad_norms.mean() - z["stats/grad_norms"].mean()) < 1e-4
+
+
+def test_acting_forward_from_context_ring(golden_dir):
+    """Batched get_action: Q of the last valid context position for windows of different lengths, incl. a wrapped ring."""
+    from dtqn_b200.agents import DtqnAgent
+    z = np.load(os.path.join(golden_dir, "acting_carflag.npz"))
+    d, layers, ctx, heads = [int(v) for v in z["meta"]]
+    steps = list(range(0, len(z["action"]), 3))
+    K = len(steps)
+    agent = DtqnAgent(lambda: _make_net(z, "policy/", "carflag"), 200 * K * 2, "cuda", 3, 200, -5, 3, False,
+                      context_len=ctx, n_envs=K)
+    cx = agent.context
+    ring = np.full((K, ctx, 3), -5.0, np.float32)
+    ts = np.zeros(K, np.int32)
+    for i, t in enumerate(steps):
+        n = int(z["ctx_len"][t])
+        win = z["ctx_obs"][t][:n].astype(np.float32)
+        # place the window in the ring with an arbitrary rotation, as the device ring would hold it
+        tstep = (n - 1) if n < ctx else (ctx - 1 + 7 * i)
+        for j in range(n):
+            ring[i, (tstep + 1 - n + j) % ctx] = win[j]
+        ts[i] = tstep
+    cx.obs.copy_(torch.from_numpy(ring)); cx.timestep_t.copy_(torch.from_numpy(ts))
+    q = agent.q_last_batched().cpu().numpy()
+    ref = z["greedy_q"][steps]
+    assert rel_err(q, ref) < Q_REL_TIGHT
+    assert np.array_equal(q.argmax(1), ref.argmax(1))
