@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- the DTQN hot path on N B200s (one process per GPU) and the reference-CPU arm.
+
+    python bench.py --gpus 1 --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # CPU port of the reference loop (oracle/loop.py)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                      # N ranks over NCCL
+
+A "step" is one iteration of the reference's training loop body (run.py:290-298) over one lockstep batch of
+environments: epsilon-greedy action through the DTQN (acting forward over the 50-token context of every env), env.step
++ TimeLimit + replay/context append (+ episode roll), then ONE DtqnAgent.train() (sample 32 windows per rank, 3 forwards,
+TD loss, backward, gradient allreduce, clip, Adam).  Workload = BASELINE.json configs[1]: DiscreteCarFlag-v0, 4096
+batched envs per GPU, ctx=50, in-embed=64, batch 32.  metric value = env-steps/s of the whole job; grad-steps/s is
+reported beside it (same timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_ID = "DiscreteCarFlag-v0"
+CTX, EMBED, HEADS, LAYERS, BATCH = 50, 64, 8, 2, 32
+FWD_FLOP_PER_TOKEN = 231_168          # SURVEY.md section 8d, CarFlag d=64 L=50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="lockstep envs per GPU")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference loop (1 env, batch 32) on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle.loop import ReferenceLoop
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lp = ReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX, batch=args.batch)
+    lp.prepopulate(8000)                      # enough completed episodes for can_sample(32); the reference uses 50k
+    for _ in range(max(3, args.warmup)):
+        lp.iteration()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lp.iteration()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "grad_steps_per_sec": v,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID}, DTQN ctx={CTX}, in-embed={EMBED}, 1 env, batch {args.batch}, reference CPU loop "
+                               "(oracle port of run.py:290-298: act + env.step + store + train per step)",
+                   "threads": cores},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} loop iterations (1 env-step + 1 grad-step each) after 8000 prepopulate steps"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from dtqn_b200 import _lib
+    from dtqn_b200.runner import BatchedTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.envs
+    tr = BatchedTrainer(ENV_ID, N, seed=1, device=dev, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX,
+                        batch=args.batch)
+    use_graph = not args.no_graph and hasattr(tr, "enable_graphs")
+    # prepopulate with the random policy until every rank can sample (>= 32 completed episodes; CarFlag episodes last
+    # up to 200 steps, so ~250 lockstep steps = ~1M transitions per rank)
+    tr.prepopulate(260)
+    assert tr.agent.replay_buffer.can_sample(args.batch)
+    if use_graph:
+        tr.enable_graphs()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        tr.train_iteration()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tr.train_iteration()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(ms.item())
+    tr.agent.check_finite()
+    env_sps = N * world * args.steps / (ms / 1e3)
+    grad_sps = args.steps / (ms / 1e3)
+
+    # ---- e2e: the same loop driven through the host-facing API with HOST buffers (pinned), copies inside the timing ----
+    q_host = torch.empty((N, tr.env.num_actions), dtype=torch.float32, pin_memory=True)
+    act_host = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+    obs_host = torch.empty((N, tr.env.obs_dim), dtype=torch.float32, pin_memory=True)
+    rew_host = torch.empty((N,), dtype=torch.float32, pin_memory=True)
+    done_host = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
+    loss_host = torch.empty((8,), dtype=torch.float32, pin_memory=True)
+    hrng = np.random.default_rng(1234 + rank)
+    h2d = act_host.numel() * 4
+    d2h = q_host.numel() * 4 + obs_host.numel() * 4 + rew_host.numel() * 4 + done_host.numel() + loss_host.numel() * 4
+
+    def e2e_step(eps):
+        q = tr.agent.q_last_batched()                              # acting forward on the device context
+        q_host.copy_(q, non_blocking=True); torch.cuda.synchronize()
+        greedy = q_host.numpy().argmax(1).astype(np.int32)          # host-side epsilon-greedy (user policy code)
+        explore = hrng.random(N) < eps
+        act_host.numpy()[:] = np.where(explore, hrng.integers(0, tr.env.num_actions, N), greedy)
+        tr.env.step(actions=act_host.to(dev, non_blocking=True), mode=_lib.ACT_GIVEN)
+        obs_host.copy_(tr.env.obs_out, non_blocking=True); rew_host.copy_(tr.env.reward_out, non_blocking=True)
+        done_host.copy_(tr.env.done_out, non_blocking=True)
+        tr.agent.train()
+        loss_host.copy_(tr.agent.stats, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(loss_host[0])
+
+    if use_graph:
+        tr.disable_graphs()
+    for _ in range(3):
+        e2e_step(tr.eps.val)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(10, args.steps // 2)
+    for _ in range(e2e_steps):
+        e2e_step(tr.eps.val)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = N * world * e2e_steps / float(e2e_s.item())
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch of the tagged kernel, in a dedicated pass ----
+    roof = None
+    launches = None
+    if rank == 0:
+        lib = _lib.lib
+        lib.dtqn_profile_enable.argtypes = [C.c_int32]
+        lib.dtqn_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        lib.dtqn_profile_enable(1)
+        psteps = min(10, args.steps)
+        for _ in range(psteps):
+            tr.train_iteration()
+        torch.cuda.synchronize()
+        tags = {}
+        names = ["linear_fwd", "attn_fwd", "env_step", "env_roll", "replay_gather", "dgrad", "wgrad", "attn_bwd", "ln_bwd",
+                 "embed", "head", "td_loss", "clip_adam", "other"]
+        for t, nm in enumerate(names):
+            ms_t, n_t, w_t = C.c_double(), C.c_int64(), C.c_double()
+            lib.dtqn_profile_read(t, C.byref(ms_t), C.byref(n_t), C.byref(w_t))
+            if n_t.value:
+                tags[nm] = dict(ms=ms_t.value, n=n_t.value, work=w_t.value)
+        lib.dtqn_profile_enable(0)
+        pk = peaks()
+        dom = max(tags.items(), key=lambda kv: kv[1]["ms"]) if tags else None
+        if dom is not None:
+            nm, v = dom
+            tensor = nm in ("linear_fwd", "dgrad", "wgrad", "attn_fwd", "attn_bwd", "linear_tc")
+            if tensor:
+                ach = v["work"] / (v["ms"] * 1e-3) / 1e12
+                roof = {"kernel": nm, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                        "launches_timed": v["n"], "avg_us_per_launch": 1e3 * v["ms"] / v["n"]}
+            else:
+                ach = v["work"] / (v["ms"] * 1e-3) / 1e9
+                roof = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                        "launches_timed": v["n"], "avg_us_per_launch": 1e3 * v["ms"] / v["n"]}
+            roof["per_kernel_share_of_timed_ms"] = {k: round(x["ms"] / sum(y["ms"] for y in tags.values()), 4) for k, x in tags.items()}
+            for k in ("env_step", "replay_gather"):
+                if k in tags:
+                    roof[k + "_GBps"] = tags[k]["work"] / (tags[k]["ms"] * 1e-3) / 1e9
+        launches = int(sum(v["n"] for v in tags.values()) / max(1, psteps)) if tags else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.loop import ReferenceLoop
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        lp = ReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX, batch=args.batch)
+        lp.prepopulate(8000)
+        for _ in range(5):
+            lp.iteration()
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < 12.0:
+            lp.iteration(); n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "env-steps/s", "grad_steps_per_sec": n / dt, "cores": cores, "kind": "port",
+               "sample": f"{n} iterations of the 1-env reference loop (1 env-step + 1 grad-step, batch {args.batch}) in {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "env_steps_per_sec", "value": env_sps, "unit": "env-steps/s", "grad_steps_per_sec": grad_sps,
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID}, {N} batched envs per GPU, ctx={CTX}, in-embed={EMBED}, heads={HEADS}, "
+                                   f"layers={LAYERS}, train batch {args.batch} windows per GPU, policy-in-the-loop "
+                                   "(eps-greedy through the DTQN), 1 grad step per lockstep env step",
+                       "envs_per_gpu": N, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (acting-forward activations, ~600 MB) exceeds the 126 MB L2; no flush",
+                       "cuda_graphs": bool(use_graph)},
+            "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
+                                                "host obs/reward/done -> agent.train -> host loss"},
+            "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,7 +40,8 @@ class ContextStruct(C.Structure):
 
 class StepIO(C.Structure):
     _fields_ = [("action_mode", C.c_int32), ("epsilon", C.c_float), ("actions", _p), ("q_last", _p),
-                ("obs_out", _p), ("reward_out", _p), ("done_out", _p), ("truncated_out", _p), ("success_out", _p)]
+                ("obs_out", _p), ("reward_out", _p), ("done_out", _p), ("truncated_out", _p), ("success_out", _p),
+                ("epsilon_dev", _p)]
 
 
 class DtqnLibError(RuntimeError):

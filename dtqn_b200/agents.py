@@ -142,15 +142,20 @@ class DtqnAgent:
         forward_groups(net, [net.flat], [src], self.n_envs, self.context_len, q_mode=1, save=0, q_out=self._q_last)
         return self._q_last
 
-    def act_and_step(self, env, epsilon: float, record: Optional[bool] = None) -> None:
+    def act_and_step(self, env, epsilon: float, record: Optional[bool] = None, epsilon_dev=None) -> None:
         """run.step (run.py:356-377) for all envs: acting forward -> eps-greedy -> env.step -> observe."""
         q = self.q_last_batched()
         rec = (self.train_mode == TrainMode.TRAIN) if record is None else record
-        env.step(mode=_lib.ACT_EPS_GREEDY, epsilon=epsilon, q_last=q, record=rec)
+        env.step(mode=_lib.ACT_EPS_GREEDY, epsilon=epsilon, q_last=q, record=rec, epsilon_dev=epsilon_dev)
 
     # ---- training step (agents/dtqn.py:162-269) ----------------------------------------------------------------------------
     def train_on_windows(self, obs_win, act_win, rew, done) -> None:
         """3 forwards + TD loss + backward + (allreduce) + clip + Adam on gathered (L+1)-row windows."""
+        self.forward_backward(obs_win, act_win, rew, done)
+        self.reduce_and_step()
+        self.finish_step()
+
+    def forward_backward(self, obs_win, act_win, rew, done) -> None:
         net, tgt = self.policy_network, self.target_network
         B, L, O = obs_win.shape[0], self.context_len, self.env_obs_length
         stride = (L + 1) * O
@@ -163,14 +168,22 @@ class DtqnAgent:
                                        act_win.data_ptr(), rew.data_ptr(), done.data_ptr(), B, L, self.history,
                                        self.gamma, ws.data_ptr(), ws.numel(), self._td_scratch.data_ptr(),
                                        self.grads.data_ptr(), self.stats.data_ptr(), st), "dtqn_td_backward")
+
+    def reduce_and_step(self) -> None:
+        """Gradient allreduce (the one collective, only when world > 1) -> /world -> global-norm clip -> Adam, identical
+        on every rank."""
+        net, st = self.policy_network, _lib.stream_ptr()
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if world > 1:
-            dist.all_reduce(self.grads)                      # the one collective: sum of per-rank mean-MSE gradients
+            dist.all_reduce(self.grads)                      # sum of per-rank mean-MSE gradients
         _lib.check(_l.dtqn_clip_adam(net.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), net.n_flat, 1.0 / world, self.grad_norm_clip,
                                      self.learning_rate, self.betas[0], self.betas[1], self.adam_eps,
                                      self.opt_step.data_ptr(), self.opt_scratch.data_ptr(), self.stats.data_ptr(),
                                      self.flags.data_ptr(), self.stats_ring.data_ptr(), RING, st), "dtqn_clip_adam")
+
+    def finish_step(self) -> None:
+        """Host-side bookkeeping of one update (agents/dtqn.py:266-269)."""
         self.num_train_steps += 1
         if self.strict_finite:
             self.check_finite()

@@ -12,6 +12,7 @@
 //                     the CTA counts), env.reset(), ReplayBuffer.store_obs, Context.reset.
 #include "common.cuh"
 #include "pcg64.cuh"
+#include "prof.cuh"
 
 #define ENV_THREADS 256
 
@@ -121,7 +122,8 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
                 a = (int)ag.bounded(A);
             } else {
                 double u = ag.next_double();
-                if (u < (double)io.epsilon) {
+                const float eps = io.epsilon_dev ? *io.epsilon_dev : io.epsilon;
+                if (u < (double)eps) {
                     a = (int)ag.bounded(A);
                 } else {                                               // torch.argmax: first maximal index
                     const float* q = io.q_last + (size_t)i * A;
@@ -358,15 +360,21 @@ extern "C" int dtqn_env_step(const dtqn_env* env, const dtqn_replay* rb, const d
     dtqn_replay rbv = rb ? *rb : dtqn_replay{};
     dtqn_context cxv = cx ? *cx : dtqn_context{};
     const int grid = dtqn_cdiv(env->n_envs, ENV_THREADS);
-    if (env->kind == DTQN_ENV_CARFLAG) {
+    // algorithmic bytes per env-step incl. the fused replay append: 55 B CarFlag, 140 B Memory
+    const double step_bytes = (env->kind == DTQN_ENV_CARFLAG ? 55.0 : 140.0) * env->n_envs;
+    prof_begin(PROF_ENV_STEP, st);
+    if (env->kind == DTQN_ENV_CARFLAG)
         env_step_kernel<DTQN_ENV_CARFLAG><<<grid, ENV_THREADS, 0, st>>>(*env, rbv, cxv, *io, rb != nullptr, cx != nullptr);
-        DTQN_LAUNCH_CHECK();
-        env_roll_kernel<DTQN_ENV_CARFLAG><<<grid, ENV_THREADS, 0, st>>>(*env, rbv, cxv, rb != nullptr, cx != nullptr);
-    } else {
+    else
         env_step_kernel<DTQN_ENV_MEMORY><<<grid, ENV_THREADS, 0, st>>>(*env, rbv, cxv, *io, rb != nullptr, cx != nullptr);
-        DTQN_LAUNCH_CHECK();
+    prof_end(PROF_ENV_STEP, st, step_bytes);
+    DTQN_LAUNCH_CHECK();
+    prof_begin(PROF_ENV_ROLL, st);
+    if (env->kind == DTQN_ENV_CARFLAG)
+        env_roll_kernel<DTQN_ENV_CARFLAG><<<grid, ENV_THREADS, 0, st>>>(*env, rbv, cxv, rb != nullptr, cx != nullptr);
+    else
         env_roll_kernel<DTQN_ENV_MEMORY><<<grid, ENV_THREADS, 0, st>>>(*env, rbv, cxv, rb != nullptr, cx != nullptr);
-    }
+    prof_end(PROF_ENV_ROLL, st, 0.0);
     DTQN_LAUNCH_CHECK();
     return 0;
 }

@@ -3,6 +3,7 @@
 // All gradients are derived by hand for the forward in net_fwd.cu; parity is against torch autograd on the oracle.
 #include "net.cuh"
 #include "gemm_simt.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -387,9 +388,11 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
 template <int EPI>
 int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
     dim3 grid(dtqn_cdiv(T, GEMM_BM), 1, 1);
+    prof_begin(PROF_DGRAD, st);
     if (Kf % 128 == 0) { grid.y = Kf / 128; dgrad_kernel<128, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
     else if (Kf % 64 == 0) { grid.y = Kf / 64; dgrad_kernel<64, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
     else return DTQN_E_UNSUPPORTED;
+    prof_end(PROF_DGRAD, st, 2.0 * (double)T * Nf * Kf);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -397,7 +400,9 @@ int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, i
 int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gW, float* gb, cudaStream_t st) {
     if (Nf % 64 || Kf % 64) return DTQN_E_UNSUPPORTED;
     dim3 grid(Nf / 64, Kf / 64, dtqn_cdiv(T, WG_CHUNK));
+    prof_begin(PROF_WGRAD, st);
     wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gW, gb);
+    prof_end(PROF_WGRAD, st, 2.0 * (double)T * Nf * Kf);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -446,12 +451,16 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     cudaError_t ce = cudaMemsetAsync(grads, 0, sizeof(float) * lay.total, st);
     if (ce != cudaSuccess) return (int)ce;
 
+    prof_begin(PROF_TD, st);
     td_loss_kernel<<<dtqn_cdiv(T0, 256), 256, 0, st>>>(q_all, act_win, rew, done, B, L, A, history, gamma, s.dq,
                                                         s.partial, s.ticket, stats_out);
+    prof_end(PROF_TD, st, 0.0);
     DTQN_LAUNCH_CHECK();
     // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
+    prof_begin(PROF_HEAD, st);
     head_bwd_kernel<<<dtqn_cdiv(T0, 64), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
                                                         grads + lay.h2_w, grads + lay.h2_b);
+    prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();
     const float* x_last = act.layer[cfg->n_layers - 1].x2;
     if ((rc = launch_wgrad(s.g_hh, x_last, Ti, d, d, grads + lay.h1_w, grads + lay.h1_b, st))) return rc;
@@ -461,8 +470,10 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         const LayerAct& la = act.layer[li];
         const float* x_in = li == 0 ? act.x0 : act.layer[li - 1].x2;
         // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
+        prof_begin(PROF_LN_BWD, st);
         if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
         else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
+        prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // ffn.2
         if ((rc = launch_wgrad(s.ga, la.h, Ti, d, 4 * d, grads + lo.f2_w, grads + lo.f2_b, st))) return rc;
@@ -471,8 +482,10 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         if ((rc = launch_wgrad(s.gh, la.x1, Ti, 4 * d, d, grads + lo.f1_w, grads + lo.f1_b, st))) return rc;
         if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
         // LN1 backward: dy = gx1 -> gu (du1), ga (d out_proj output)
+        prof_begin(PROF_LN_BWD, st);
         if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
         else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
+        prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // out_proj
         if ((rc = launch_wgrad(s.ga, la.o, Ti, d, d, grads + lo.out_w, grads + lo.out_b, st))) return rc;
@@ -482,10 +495,12 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
             dim3 grid(H, (unsigned)B);
             const int thr = L <= 64 ? 64 : 128;
             const float scale = 1.0f / sqrtf((float)hd);
+            prof_begin(PROF_ATTN_BWD, st);
             if (hd == 8) attn_bwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
             else if (hd == 16) attn_bwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
             else if (hd == 4) attn_bwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
             else return DTQN_E_UNSUPPORTED;
+            prof_end(PROF_ATTN_BWD, st, 8.0 * (double)T0 * L * d);
             DTQN_LAUNCH_CHECK();
         }
         // in_proj
@@ -493,6 +508,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
     }
     // embedding + position table
+    prof_begin(PROF_OTHER, st);
     if (cfg->pos_trainable) {
         pos_bwd_kernel<<<dtqn_cdiv((long long)L * d, 256), 256, 0, st>>>(s.gx, B, L, d, grads + lay.pos);
         DTQN_LAUNCH_CHECK();
@@ -505,5 +521,6 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
                                                               grads + lay.emb_w, grads + lay.emb_b);
         DTQN_LAUNCH_CHECK();
     }
+    prof_end(PROF_OTHER, st, 0.0);
     return 0;
 }

@@ -8,6 +8,7 @@
 //   head_kernel       final Linear(d, A) (dtqn.py:149-153), one warp per token
 #include "net.cuh"
 #include "gemm_simt.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -254,6 +255,7 @@ head_kernel(const float* __restrict__ hh, GroupPtrs P, long long w_off, long lon
 template <int EPI>
 int launch_linear(const LinArgs& a, int G, int d_model, cudaStream_t st) {
     dim3 grid(dtqn_cdiv(a.Tg, GEMM_BM), 1, G);
+    prof_begin(PROF_LINEAR, st);
     if (EPI == EPI_RES_LN) {
         if (a.N == 64) linear_kernel<64, EPI_RES_LN><<<grid, GEMM_THREADS, 0, st>>>(a);
         else if (a.N == 128) linear_kernel<128, EPI_RES_LN><<<grid, GEMM_THREADS, 0, st>>>(a);
@@ -263,6 +265,7 @@ int launch_linear(const LinArgs& a, int G, int d_model, cudaStream_t st) {
         else if (a.N % 64 == 0) { grid.y = a.N / 64; linear_kernel<64, EPI><<<grid, GEMM_THREADS, 0, st>>>(a); }
         else return DTQN_E_UNSUPPORTED;
     }
+    prof_end(PROF_LINEAR, st, 2.0 * (double)a.Tg * G * a.N * a.K);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -322,8 +325,10 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     }
     {
         dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
+        prof_begin(PROF_EMBED, st);
         embed_kernel<<<grid, 256, 0, st>>>(P, S, *cfg, lay.emb_table, lay.emb_w, lay.emb_b, lay.pos, n_seq, L,
                                             cfg->discrete ? (float)(cfg->vocab - 1) : -5.0f, act.x0);
+        prof_end(PROF_EMBED, st, 2.0 * (double)T * lay.k_in * d);
         DTQN_LAUNCH_CHECK();
     }
     const float* x_in = act.x0;
@@ -340,11 +345,13 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
             dim3 grid(H, (unsigned)(n_seq * G));
             const int thr = L <= 64 ? 64 : 128;
             const float scale = 1.0f / sqrtf((float)hd);
+            prof_begin(PROF_ATTN_FWD, st);
             if (hd == 8) attn_fwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
             else if (hd == 16) attn_fwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
             else if (hd == 32) attn_fwd_kernel<32><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
             else if (hd == 4) attn_fwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
             else return DTQN_E_UNSUPPORTED;
+            prof_end(PROF_ATTN_FWD, st, 4.0 * (double)T * L * d);      // dense L x L count, as the reference computes it
             DTQN_LAUNCH_CHECK();
         }
         // out_proj -> relu -> +x -> LN1
@@ -369,7 +376,9 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         // only the last valid position feeds the head; qkv of layer 0 is free scratch by now
         float* xl = act.layer[0].qkv;
         dim3 grid(dtqn_cdiv((long long)n_seq * d, 256), 1, G);
+        prof_begin(PROF_OTHER, st);
         gather_last_kernel<<<grid, 256, 0, st>>>(x_in, S, n_seq, L, d, xl);
+        prof_end(PROF_OTHER, st, 0.0);
         DTQN_LAUNCH_CHECK();
         head_in = xl; Th = n_seq;
     }
@@ -378,7 +387,9 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.P = P; a.Tg = (int)Th; a.X = head_in; a.Y = act.hh; a.w_off = lay.h1_w; a.b_off = lay.h1_b; a.N = d; a.K = d;
         if ((rc = launch_linear<EPI_BIAS_RELU>(a, G, d, st))) return rc;
         dim3 grid(dtqn_cdiv(Th, 8), 1, G);
+        prof_begin(PROF_HEAD, st);
         head_kernel<<<grid, 256, 0, st>>>(act.hh, P, lay.h2_w, lay.h2_b, Th, d, cfg->num_actions, q_out);
+        prof_end(PROF_HEAD, st, 2.0 * (double)Th * G * d * cfg->num_actions);
         DTQN_LAUNCH_CHECK();
     }
     return 0;

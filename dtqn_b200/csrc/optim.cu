@@ -3,6 +3,7 @@
 // second kernel re-reduces the partial sums in a fixed order, so the result is deterministic and identical on all CTAs
 // (and, after the gradient allreduce, on all ranks).
 #include "common.cuh"
+#include "prof.cuh"
 
 #define OPT_THREADS 256
 #define OPT_MAX_BLOCKS 512
@@ -82,11 +83,13 @@ extern "C" int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float
     int blocks = dtqn_cdiv(n, OPT_THREADS * 4);
     if (blocks > OPT_MAX_BLOCKS) blocks = OPT_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
+    prof_begin(PROF_ADAM, st);
     sqnorm_kernel<<<blocks, OPT_THREADS, 0, st>>>(grads, n, grad_scale, scratch, (long long*)step_counter);
     DTQN_LAUNCH_CHECK();
     clip_adam_kernel<<<blocks, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1,
                                                     beta2, eps, (const long long*)step_counter, scratch, blocks,
                                                     stats_out, flags_out, stats_ring, stats_ring ? ring_len : 1);
+    prof_end(PROF_ADAM, st, 32.0 * (double)n);     // 28 B/param Adam + 4 B/param norm pass
     DTQN_LAUNCH_CHECK();
     return 0;
 }

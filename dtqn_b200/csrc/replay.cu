@@ -2,6 +2,7 @@
 // Restates dtqn/buffers/replay_buffer.py:137-168 (ReplayBuffer.sample).  The store / flush side is fused into the
 // env step kernels (env.cu).
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -87,7 +88,9 @@ extern "C" int dtqn_replay_sample_indices(const dtqn_replay* rb, int32_t batch, 
                                           void* stream) {
     if (!rb || batch <= 0 || !episodes_out || !starts_out || !rb->counters || !rb->slot_open || !rb->episode_lengths)
         return DTQN_E_ARG;
+    prof_begin(PROF_OTHER, (cudaStream_t)stream);
     sample_indices_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*rb, batch, seed, draw, draw_counter, episodes_out, starts_out);
+    prof_end(PROF_OTHER, (cudaStream_t)stream, 0.0);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -97,7 +100,12 @@ extern "C" int dtqn_replay_gather(const dtqn_replay* rb, int32_t batch, const in
                                   void* stream) {
     if (!rb || batch <= 0 || !episodes || !starts || !obs_win || !act_win || !rew || !done) return DTQN_E_ARG;
     if (rb->context_len > rb->max_episode_steps) return DTQN_E_ARG;   // the reference's fancy index would go out of range
+    // algorithmic bytes per window: read (L+1)*O*4 + (L+1) + 4L + L + 1, write the same minus eplen
+    const double L = rb->context_len, O = rb->obs_dim;
+    const double win_bytes = 2.0 * ((L + 1) * O * 4 + (L + 1) + 4 * L + L) + 1.0;
+    prof_begin(PROF_GATHER, (cudaStream_t)stream);
     replay_gather_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(*rb, episodes, starts, obs_win, act_win, rew, done, eplen);
+    prof_end(PROF_GATHER, (cudaStream_t)stream, win_bytes * batch);
     DTQN_LAUNCH_CHECK();
     return 0;
 }

@@ -102,7 +102,8 @@ class BatchedEnv:
                    "dtqn_env_reset_all")
 
     def step(self, actions: Optional[torch.Tensor] = None, mode: Optional[int] = None, epsilon: float = 0.0,
-             q_last: Optional[torch.Tensor] = None, record: bool = True) -> None:
+             q_last: Optional[torch.Tensor] = None, record: bool = True,
+             epsilon_dev: Optional[torch.Tensor] = None) -> None:
         """One lockstep step of every instance (run.py:356-377 fused); results land in obs_out / reward_out /
         done_out / truncated_out / success_out / actions.  ``record=False`` skips the replay (evaluation)."""
         if mode is None:
@@ -113,7 +114,8 @@ class BatchedEnv:
                          q_last=_lib.ptr(q_last) if q_last is not None else None,
                          obs_out=_lib.ptr(self.obs_out), reward_out=_lib.ptr(self.reward_out),
                          done_out=_lib.ptr(self.done_out), truncated_out=_lib.ptr(self.truncated_out),
-                         success_out=_lib.ptr(self.success_out))
+                         success_out=_lib.ptr(self.success_out),
+                         epsilon_dev=_lib.ptr(epsilon_dev) if epsilon_dev is not None else None)
         _lib.check(_lib.lib.dtqn_env_step(C.byref(self.struct), self._rb() if record else None, self._cx(),
                                           C.byref(io), _lib.stream_ptr()), "dtqn_env_step")
 

@@ -1,0 +1,127 @@
+"""Batched training loop -- the shape of run.train / run.step / run.prepopulate / run.evaluate (run.py:187-405) for
+n_envs lockstep device environments per GPU, data-parallel over ranks (one process per GPU): envs and replay are
+sharded per rank, parameters replicated, one gradient allreduce per update (agents.DtqnAgent.train_on_windows)."""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from dtqn_b200 import _lib
+from dtqn_b200.envs import BatchedEnv
+from dtqn_b200.utils import LinearAnneal, get_agent
+
+
+def rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_seed(seed: int, rank: int, n_envs: int) -> int:
+    """Rank g owns env seeds [seed + g*n_envs, seed + (g+1)*n_envs)."""
+    return seed + rank * n_envs
+
+
+class BatchedTrainer:
+    def __init__(self, env_id: str = "DiscreteCarFlag-v0", n_envs: int = 4096, seed: int = 1, device=None,
+                 inner_embed: int = 64, heads: int = 8, layers: int = 2, context: int = 50, batch: int = 32,
+                 buf_size: Optional[int] = None, lr: float = 3e-4, tuf: int = 10_000, gamma: float = 0.99,
+                 history: Optional[int] = None, num_steps: int = 2_000_000, obs_embed: int = 8,
+                 trunc_context_obs: bool = True):
+        rank, world = rank_world()
+        self.rank, self.world = rank, world
+        self.device = _lib.require_cuda(device)
+        self.env = BatchedEnv(env_id, n_envs, seed=shard_seed(seed, rank, n_envs), device=self.device)
+        self.eval_env = None
+        E = self.env.max_episode_steps
+        if buf_size is None:
+            buf_size = max(500_000, 8 * n_envs * E)           # ring >= 8 slots per env so it never wraps onto open episodes
+        torch.manual_seed(seed)                              # identical initial parameters on every rank
+        self.agent = get_agent("DTQN", [self.env], obs_embed, 0, inner_embed, buf_size, self.device, lr, batch, context,
+                               E, history or context, tuf, gamma, num_heads=heads, num_layers=layers, n_envs=n_envs,
+                               trunc_context_obs=trunc_context_obs, sample_seed=seed * 7919 + rank)
+        if world > 1:
+            dist.broadcast(self.agent.policy_network.flat, src=0)
+            self.agent.target_update()
+        self.env.attach(self.agent.replay_buffer, self.agent.train_context)
+        self.eps = LinearAnneal(1.0, 0.1, max(1, num_steps // 10))     # run.py:420
+        self.env.reset_all()                                  # run.py:287-288
+        self.n_envs = n_envs
+        self.iterations = 0
+        self._graph = None
+        self._eps_pinned = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        self._eps_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def prepopulate(self, lockstep_steps: int) -> None:
+        """run.prepopulate (run.py:380-405): uniform-random actions from the agent-side stream."""
+        for _ in range(lockstep_steps):
+            self.env.step(mode=_lib.ACT_RANDOM)
+
+    def _device_iteration(self) -> None:
+        """Everything of one loop iteration that runs on the device before the gradient collective."""
+        agent, rb = self.agent, self.agent.replay_buffer
+        self._eps_dev.copy_(self._eps_pinned, non_blocking=True)
+        agent.act_and_step(self.env, 0.0, epsilon_dev=self._eps_dev)
+        eps, starts = rb.draw_indices(agent.batch_size)
+        rb.gather_windows(eps, starts, out=agent._win)
+        agent.forward_backward(*agent._win[:4])
+        if self.world == 1:
+            agent.reduce_and_step()
+
+    def enable_graphs(self) -> None:
+        """Capture one loop iteration (acting forward, env step + roll, sample, gather, 3 forwards, TD, backward and --
+        single GPU -- clip + Adam) into a CUDA graph: ~60 launches replayed with one host call.  The per-step scalars
+        (epsilon, Adam step, sampler draw counter) live in device memory so the replay needs no re-capture."""
+        assert self.agent.replay_buffer.can_sample(self.agent.batch_size), "prepopulate before capturing"
+        self.agent.eval_off()
+        self._eps_pinned[0] = float(self.eps.val)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # warm-up on a side stream (allocations, lazy module loads)
+            self._device_iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._device_iteration()
+        self._graph = g
+        self.agent.finish_step() if self.world == 1 else (self.agent.reduce_and_step(), self.agent.finish_step())
+        self.eps.anneal()
+        self.iterations += 1
+
+    def disable_graphs(self) -> None:
+        self._graph = None
+
+    def train_iteration(self) -> None:
+        """One iteration of the run.train loop body (run.py:290-298) for all envs: step, train, anneal."""
+        if self._graph is not None:
+            self._eps_pinned[0] = float(self.eps.val)
+            self._graph.replay()
+            if self.world > 1:
+                self.agent.reduce_and_step()
+            self.agent.finish_step()
+        else:
+            self.agent.act_and_step(self.env, self.eps.val)
+            self.agent.train()
+        self.eps.anneal()
+        self.iterations += 1
+
+    @torch.no_grad()
+    def evaluate(self, eval_episodes_per_env: int = 1, max_steps: Optional[int] = None):
+        """run.evaluate (run.py:187-243): greedy policy on a separate set of envs seeded like the train envs
+        (utils/random.py:26-29), no replay writes.  Returns (success_rate, mean_return, mean_episode_length)."""
+        agent = self.agent
+        if self.eval_env is None:
+            self.eval_env = BatchedEnv(self.env.env_id, self.n_envs, seeds=self.env.seeds, device=self.device)
+            self.eval_env.attach(None, agent.eval_context)
+        ev = self.eval_env
+        agent.eval_on()
+        ev.reset_all()
+        target = eval_episodes_per_env * self.n_envs
+        steps = max_steps or (eval_episodes_per_env + 1) * ev.max_episode_steps
+        for _ in range(steps):
+            agent.act_and_step(ev, 0.0, record=False)
+        agent.eval_off()
+        ret, length, succ, n = [int(v) for v in ev.ep_stats.tolist()]
+        n = max(n, 1)
+        return succ / n, ret / n, length / n

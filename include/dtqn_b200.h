@@ -103,6 +103,7 @@ typedef struct dtqn_step_io {
     uint8_t* done_out;          /* [n] env done incl. TimeLimit; nullable */
     uint8_t* truncated_out;     /* [n] info["TimeLimit.truncated"]; nullable */
     uint8_t* success_out;       /* [n] info["is_success"]; nullable */
+    const float* epsilon_dev;   /* nullable: device scalar read instead of `epsilon` (CUDA-graph replay) */
 } dtqn_step_io;
 
 int dtqn_version(void);
@@ -198,6 +199,15 @@ int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
                    float* scratch /* >= 1024 floats */, float* stats_out, int32_t* flags_out,
                    float* stats_ring /* nullable [ring_len, 8]: row (step-1) % ring_len <- stats_out[0..8) */,
                    int32_t ring_len, void* stream);
+
+
+/* ---- measurement hooks (bench.py roofline leg; no reference analogue) --------------------------------------------
+ * When enabled, every launch of a tagged kernel is bracketed by CUDA events on its stream.  dtqn_profile_read
+ * synchronises and returns the summed duration, launch count and algorithmic work (FLOPs or bytes) of one tag.
+ * Tags: 0 linear-fwd GEMM, 1 attention-fwd, 2 env-step, 3 env-roll, 4 replay-gather, 5 dgrad, 6 wgrad, 7 attention-bwd,
+ * 8 layernorm-bwd, 9 embed, 10 head, 11 td-loss, 12 clip+adam, 13 other.  Process-global, not thread-safe. */
+int dtqn_profile_enable(int32_t on);
+int dtqn_profile_read(int32_t tag, double* total_ms, int64_t* launches, double* total_work);
 
 #ifdef __cplusplus
 }

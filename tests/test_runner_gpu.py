@@ -1,0 +1,87 @@
+"""GPU checks of the batched training loop: eager vs CUDA-graph replay agree, learning statistics are finite, evaluation
+runs without touching the replay, the host-call (reference-style) single-env API drives the same kernels."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(**kw):
+    from dtqn_b200.runner import BatchedTrainer
+    args = dict(env_id="DiscreteCarFlag-v0", n_envs=512, seed=3, device="cuda", batch=16, num_steps=10_000)
+    args.update(kw)
+    return BatchedTrainer(**args)
+
+
+def test_graph_replay_matches_eager():
+    a, b = _trainer(), _trainer()
+    for t in (a, b):
+        t.prepopulate(230)
+        assert t.agent.replay_buffer.can_sample(16)
+    b.enable_graphs()
+    a.train_iteration()            # the capture warm-up of b already performed one iteration
+    for _ in range(12):
+        a.train_iteration(); b.train_iteration()
+    torch.cuda.synchronize()
+    assert a.agent.num_train_steps == b.agent.num_train_steps == 13
+    pa, pb = a.agent.policy_network.flat, b.agent.policy_network.flat
+    assert torch.isfinite(pa).all() and torch.isfinite(pb).all()
+    # identical algorithm and random streams; only fp32 atomic accumulation order differs
+    assert (pa - pb).abs().max().item() < 5e-5
+    assert np.array_equal(a.env.rng_state(), b.env.rng_state())
+    assert abs(a.agent.td_errors.mean() - b.agent.td_errors.mean()) < 1e-4
+    assert int(a.agent.opt_step.item()) == 13 and int(b.agent.opt_step.item()) == 13
+
+
+def test_training_reduces_td_error_and_eval_runs():
+    t = _trainer(n_envs=1024, batch=32, lr=1e-3)
+    t.prepopulate(230)
+    t.enable_graphs()
+    first = None
+    for i in range(300):
+        t.train_iteration()
+        if i == 20:
+            first = t.agent.td_errors.mean()
+    last = t.agent.td_errors.mean()
+    assert np.isfinite(last) and last < first
+    before = t.agent.replay_buffer.counters.clone()
+    sr, ret, length = t.evaluate(1)
+    assert 0.0 <= sr <= 1.0 and -1.0 <= ret <= 1.0 and 1 <= length <= 200
+    assert torch.equal(before, t.agent.replay_buffer.counters)       # evaluation never writes the replay (agents/dtqn.py:159)
+
+
+def test_memory_env_trains():
+    t = _trainer(env_id="Memory-5-v0", n_envs=512, batch=16, inner_embed=128)
+    t.prepopulate(60)
+    for _ in range(5):
+        t.train_iteration()
+    t.agent.check_finite()
+    assert np.isfinite(t.agent.td_errors.mean())
+
+
+def test_host_call_api_single_env():
+    """run.py-style use: host env loop calling context_reset / get_action / observe / replay_buffer.flush / train."""
+    from dtqn_b200.utils import get_agent, set_global_seed
+    from dtqn_b200.envs import BatchedEnv
+    from oracle import envs as oenvs
+    spec = BatchedEnv("DiscreteCarFlag-v0", 1, device="cuda")           # only used for its space metadata
+    set_global_seed(1)
+    agent = get_agent("DTQN", [spec], 8, 0, 64, 20_000, "cuda", 3e-4, 4, 50, -1, 50, 10_000, 0.99, num_heads=8,
+                      num_layers=2, n_envs=1)
+    env = oenvs.make("DiscreteCarFlag-v0", 1)
+    agent.eval_off()
+    agent.context_reset(env.reset())
+    episodes = 0
+    for step in range(1400):
+        a = agent.get_action(epsilon=0.5)
+        o, r, done, info = env.step(a)
+        agent.observe(o, a, r, False if info.get("TimeLimit.truncated", False) else done)
+        if done:
+            agent.replay_buffer.flush()
+            agent.context_reset(env.reset())
+            episodes += 1
+        agent.train()
+    assert episodes >= 6 and agent.num_train_steps > 0
+    agent.check_finite()
+    assert agent.replay_buffer.pos[0] == episodes
