@@ -128,6 +128,7 @@ class DtqnAgent:
     def target_update(self) -> None:
         """Hard update (dqn.py:208-210): one flat device-to-device copy."""
         self.target_network.flat.copy_(self.policy_network.flat)
+        self.target_network.packed_stale = True
 
     def check_finite(self) -> None:
         if int(self.flags.item()) != 0:
@@ -139,7 +140,7 @@ class DtqnAgent:
         cx, net = self.context, self.policy_network
         src = ObsSrc(obs=cx.obs.data_ptr(), seq_stride=cx.max_length * cx.env_obs_length,
                      timestep=cx.timestep_t.data_ptr(), ring_len=cx.max_length, _pad=0)
-        forward_groups(net, [net.flat], [src], self.n_envs, self.context_len, q_mode=1, save=0, q_out=self._q_last)
+        forward_groups(net, [net], [src], self.n_envs, self.context_len, q_mode=1, save=0, q_out=self._q_last)
         return self._q_last
 
     def act_and_step(self, env, epsilon: float, record: Optional[bool] = None, epsilon_dev=None) -> None:
@@ -161,7 +162,7 @@ class DtqnAgent:
         stride = (L + 1) * O
         s_obs = ObsSrc(obs=obs_win.data_ptr(), seq_stride=stride, timestep=None, ring_len=0, _pad=0)
         s_next = ObsSrc(obs=obs_win.data_ptr() + 4 * O, seq_stride=stride, timestep=None, ring_len=0, _pad=0)
-        ws = forward_groups(net, [net.flat, net.flat, tgt.flat], [s_obs, s_next, s_next], B, L, q_mode=0, save=1,
+        ws = forward_groups(net, [net, net, tgt], [s_obs, s_next, s_next], B, L, q_mode=0, save=1,
                             q_out=self._q_all)
         st = _lib.stream_ptr()
         _lib.check(_l.dtqn_td_backward(C.byref(net.cfg), net.flat.data_ptr(), C.byref(s_obs), self._q_all.data_ptr(),
@@ -181,6 +182,7 @@ class DtqnAgent:
                                      self.learning_rate, self.betas[0], self.betas[1], self.adam_eps,
                                      self.opt_step.data_ptr(), self.opt_scratch.data_ptr(), self.stats.data_ptr(),
                                      self.flags.data_ptr(), self.stats_ring.data_ptr(), RING, st), "dtqn_clip_adam")
+        net.repack()                                         # refresh the tensor-core weight image (1 launch)
 
     def finish_step(self) -> None:
         """Host-side bookkeeping of one update (agents/dtqn.py:266-269)."""

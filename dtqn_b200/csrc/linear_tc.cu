@@ -1,0 +1,395 @@
+// tcgen05 (5th-gen tensor core) Linear for the large-M forward GEMMs of the DTQN hot path: the acting forward over
+// n_envs x ctx tokens (QKV / out_proj / FFN projections, the only dense contractions -- transformer.py:64-77).
+//
+//   Y[128-token tile, N_TILE] = epi( X[128, K] W[N_TILE, K]^T + b )
+//
+// * fp32 parity on bf16 tensor cores: every operand is split x = hi + lo (two bf16), and three MMAs per k-step
+//   accumulate hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator (error ~2^-16 per product; measured against the
+//   1e-3 bar in tests).  Tensor-pipe utilisation is therefore capped at 1/3 on algorithmic FLOPs.
+// * weights are pre-split and pre-tiled ("packed") by pack_weights_kernel into the exact shared-memory image of a
+//   K-major SWIZZLE_NONE UMMA operand, so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per k-chunk brings a
+//   [N_TILE x 64] hi+lo block in; activations are loaded fp32 (coalesced), split in registers and written to the
+//   canonical layout by all 128 threads.
+// * one elected thread issues tcgen05.mma (cta_group::1, M=128); tcgen05.commit signals an mbarrier; the epilogue reads
+//   the accumulator with tcgen05.ld 32x32b (thread = row), so bias / ReLU / residual / LayerNorm are thread-local.
+// * single smem stage per CTA, 2-3 CTAs per SM (TMEM 64..256 of 512 columns each) overlap each other's load / MMA /
+//   epilogue phases.
+#include "net.cuh"
+#include "prof.cuh"
+#include "linear_tc.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int TC_M = 128;                 // rows per tile = UMMA M
+constexpr int TC_KC = 64;                 // K elements per smem stage
+constexpr int A_CHUNK_STRIDE = TC_M * 16 + 16;   // bytes between 8-element k-chunks of the A tile (+16: conflict-free stores)
+constexpr int A_HALF_BYTES = (TC_KC / 8) * A_CHUNK_STRIDE;   // one of hi / lo
+
+__device__ int g_tc_error = 0;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// bounded wait: a mis-programmed TMA / MMA must never hang the GPU; on timeout flag the error and let the CTA drain
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int i = 0; i < (1 << 20); ++i)
+        if (mbar_try_wait(bar, parity)) return true;
+    atomicExch(&g_tc_error, 1);
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start >> 4 at [0,14),
+// leading (k-chunk) byte offset >> 4 at [16,30), stride (8-row group) byte offset >> 4 at [32,46), version 1 at [46,48).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32 (1 @ [4,6)), A = B = BF16 (1 @ [7,10), [10,13)), K-major both, N >> 3 @ [17,23),
+// M >> 4 @ [24,29).
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 8 floats -> two 16-byte chunks
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[i] = __float2bfloat16_rn(x[i]);
+        l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
+    }
+    hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------------------------
+// W[N, K] fp32 row-major -> blocks [n_tile][k_chunk] of { hi[8][N_TILE][8 bf16], lo[8][N_TILE][8 bf16] }.
+__global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, TcPackTable tab) {
+    const TcPackEntry e = tab.e[blockIdx.y];
+    const int NT = e.n_tile;
+    const long long chunks = (long long)e.N * (e.K / 8);          // 16-byte chunks per half
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx / (e.K / 8)), kc8 = (int)(idx % (e.K / 8));
+        const float* src = params + e.w_off + (long long)n * e.K + kc8 * 8;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = src[i];
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const int nt = n / NT, nl = n % NT, kc = (kc8 * 8) / TC_KC, c = kc8 % (TC_KC / 8);
+        const long long blk = ((long long)nt * (e.K / TC_KC) + kc) * ((long long)NT * TC_KC * 4);
+        uint8_t* dst = packed + e.pk_off + blk + ((long long)c * NT + nl) * 16;
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + (long long)NT * TC_KC * 2) = lo;
+    }
+}
+
+// ---- the GEMM -----------------------------------------------------------------------------------------------------------------
+struct TcArgs {
+    LinArgs a;
+    const uint8_t* packed[DTQN_MAX_GROUPS];
+    long long pk_off;
+};
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(128)
+linear_tc_kernel(TcArgs t) {
+    extern __shared__ uint8_t smem_raw[];
+    const LinArgs& a = t.a;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.z, m0 = blockIdx.x * TC_M, nt = blockIdx.y;
+    constexpr int TMEM_COLS = N_TILE <= 64 ? 64 : (N_TILE <= 128 ? 128 : 256);
+    constexpr uint32_t B_HALF = N_TILE * TC_KC * 2;               // bytes of one of hi / lo of a weight block
+
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                                            // hi then lo, A_HALF_BYTES each
+    uint8_t* sB = base + ((2 * A_HALF_BYTES + 1023) & ~1023);      // hi then lo, B_HALF each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * B_HALF); // [0] weights landed, [1] MMAs retired
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
+    __shared__ int s_fail;
+    const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_mma, 1);
+        s_fail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    const size_t grow = (size_t)g * a.Tg;
+    const float* X = a.X + grow * a.K;
+    const int n_it = a.K / TC_KC;
+    const uint8_t* wblk = t.packed[g] + t.pk_off + (size_t)nt * n_it * (2 * B_HALF);
+    const uint32_t idesc = umma_idesc(TC_M, N_TILE);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    bool ok = true;
+
+    for (int it = 0; it < n_it; ++it) {
+        if (it > 0) ok = ok && mbar_wait(bar_mma, (uint32_t)((it - 1) & 1));   // smem stage free again
+        if (tid == 0 && ok) {
+            mbar_expect_tx(bar_b, 2 * B_HALF);
+            bulk_g2s(sB_u, wblk + (size_t)it * (2 * B_HALF), 2 * B_HALF, bar_b);
+        }
+        // activations: 16 rows x 64 floats per pass; a warp reads 4 rows x 256 B (coalesced), splits, stores conflict-free
+#pragma unroll
+        for (int p = 0; p < TC_M / 16; ++p) {
+            const int r = p * 16 + (tid >> 3), c = tid & 7;
+            float x[8];
+            if (m0 + r < a.Tg) {
+                const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + it * TC_KC + c * 8);
+                const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = 0.f;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(sA + c * A_CHUNK_STRIDE + r * 16) = hi;
+            *reinterpret_cast<uint4*>(sA + A_HALF_BYTES + c * A_CHUNK_STRIDE + r * 16) = lo;
+        }
+        fence_async_smem();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0 && ok) {
+            if (mbar_wait(bar_b, (uint32_t)(it & 1))) {
+                tc_fence_after();
+#pragma unroll
+                for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+                    const uint64_t a_hi = umma_desc(sA_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                    const uint64_t a_lo = umma_desc(sA_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                    const uint64_t b_hi = umma_desc(sB_u + k16 * 2 * (N_TILE * 16), N_TILE * 16, 128);
+                    const uint64_t b_lo = umma_desc(sB_u + B_HALF + k16 * 2 * (N_TILE * 16), N_TILE * 16, 128);
+                    umma_bf16(tmem, a_hi, b_hi, idesc, (it | k16) ? 1u : 0u);
+                    umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+                    umma_bf16(tmem, a_lo, b_hi, idesc, 1u);
+                }
+                umma_commit(bar_mma);         // arrives when every MMA issued so far has retired
+            } else s_fail = 1;
+        }
+    }
+    ok = ok && mbar_wait(bar_mma, (uint32_t)((n_it - 1) & 1));
+    __syncthreads();
+    ok = ok && !s_fail;
+    tc_fence_after();
+
+    if (ok) {
+        const int r = m0 + warp * 32 + lane;                        // TMEM lane == tile row
+        const bool row_ok = r < a.Tg;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float* p = a.P.p[g];
+        const int n0 = nt * N_TILE;
+        if (EPI != EPI_RES_LN) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                if (row_ok) {
+                    float* y = a.Y + (grow + r) * (size_t)a.N + n0 + c0;
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            o[i] = v[q + i] + __ldg(p + a.b_off + n0 + c0 + q + i);
+                            if (EPI == EPI_BIAS_RELU) o[i] = fmaxf(o[i], 0.f);
+                        }
+                        *reinterpret_cast<float4*>(y + q) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+        } else {
+            // x_out = LayerNorm(x_res + relu(acc + b)); the whole row (N_TILE == d_model) lives in this thread
+            float u[N_TILE];
+            const size_t ro = (grow + (row_ok ? r : 0)) * (size_t)N_TILE;
+            float s = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+#pragma unroll
+                for (int q = 0; q < 16; q += 4) {
+                    const float4 xr = *reinterpret_cast<const float4*>(a.R + ro + c0 + q);
+                    const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+                    float rl[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rl[i] = fmaxf(v[q + i] + __ldg(p + a.b_off + c0 + q + i), 0.f);
+                        u[c0 + q + i] = xv[i] + rl[i];
+                        s += u[c0 + q + i];
+                    }
+                    if (a.r_save && row_ok)
+                        *reinterpret_cast<float4*>(a.r_save + ro + c0 + q) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+                }
+            }
+            const float mean = s * (1.f / N_TILE);
+            float vs = 0.f;
+#pragma unroll
+            for (int j = 0; j < N_TILE; ++j) { const float dl = u[j] - mean; vs = fmaf(dl, dl, vs); }
+            const float rstd = 1.0f / sqrtf(vs * (1.f / N_TILE) + 1e-5f);
+            if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < N_TILE; q += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        o[i] = (u[q + i] - mean) * rstd * __ldg(p + a.gamma_off + q + i) + __ldg(p + a.beta_off + q + i);
+                    *reinterpret_cast<float4*>(a.Y + ro + q) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                if (a.st_save) { a.st_save[(grow + r) * 2] = mean; a.st_save[(grow + r) * 2 + 1] = rstd; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+template <int N_TILE, int EPI>
+int launch_one(const TcArgs& t, int G, cudaStream_t st) {
+    constexpr size_t smem = 1024 + ((2 * A_HALF_BYTES + 1023) & ~1023) + 2 * (size_t)N_TILE * TC_KC * 2 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<N_TILE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid(dtqn_cdiv(t.a.Tg, TC_M), t.a.N / N_TILE, G);
+    linear_tc_kernel<N_TILE, EPI><<<grid, 128, smem, st>>>(t);
+    return 0;
+}
+
+}  // namespace
+
+int tc_ntile(int N) {
+    switch (N) {
+        case 64: return 64; case 128: return 128; case 192: return 192; case 256: return 256;
+        case 384: return 192; case 512: return 256; default: return 0;
+    }
+}
+
+int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab) {
+    const int d = c.d_model;
+    long long off = 0;
+    int n = 0;
+    auto add = [&](long long w_off, int N, int K) {
+        TcPackEntry& e = tab.e[n++];
+        e.w_off = w_off; e.N = N; e.K = K; e.n_tile = tc_ntile(N); e.pk_off = off;
+        off += (long long)N * K * 4;
+    };
+    for (int i = 0; i < c.n_layers; ++i) {
+        const LayerOff& l = lay.layer[i];
+        add(l.in_w, 3 * d, d); add(l.out_w, d, d); add(l.f1_w, 4 * d, d); add(l.f2_w, d, 4 * d);
+    }
+    add(lay.h1_w, d, d);
+    tab.n = n; tab.total_bytes = off;
+    return 0;
+}
+
+int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st) {
+    TcArgs t{};
+    t.a = a; t.pk_off = pk_off;
+    for (int g = 0; g < G; ++g) t.packed[g] = packed[g];
+    const int nt = tc_ntile(a.N);
+    if (!nt || a.K % TC_KC) return DTQN_E_UNSUPPORTED;
+    int rc = DTQN_E_UNSUPPORTED;
+    prof_begin(PROF_LINEAR, st);
+    if (epi == EPI_RES_LN) {
+        if (a.N == 64) rc = launch_one<64, EPI_RES_LN>(t, G, st);
+        else if (a.N == 128) rc = launch_one<128, EPI_RES_LN>(t, G, st);
+    } else if (epi == EPI_BIAS) {
+        if (nt == 64) rc = launch_one<64, EPI_BIAS>(t, G, st);
+        else if (nt == 128) rc = launch_one<128, EPI_BIAS>(t, G, st);
+        else if (nt == 192) rc = launch_one<192, EPI_BIAS>(t, G, st);
+        else rc = launch_one<256, EPI_BIAS>(t, G, st);
+    } else {
+        if (nt == 64) rc = launch_one<64, EPI_BIAS_RELU>(t, G, st);
+        else if (nt == 128) rc = launch_one<128, EPI_BIAS_RELU>(t, G, st);
+        else if (nt == 192) rc = launch_one<192, EPI_BIAS_RELU>(t, G, st);
+        else rc = launch_one<256, EPI_BIAS_RELU>(t, G, st);
+    }
+    prof_end(PROF_LINEAR, st, 2.0 * (double)a.Tg * G * a.N * a.K);
+    if (rc) return rc;
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg) {
+    if (!cfg) return DTQN_E_ARG;
+    NetLayout lay;
+    int rc = net_layout(*cfg, lay);
+    if (rc) return rc;
+    TcPackTable tab;
+    tc_pack_table(*cfg, lay, tab);
+    return tab.total_bytes;
+}
+
+extern "C" int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed, void* stream) {
+    if (!cfg || !params || !packed) return DTQN_E_ARG;
+    NetLayout lay;
+    int rc = net_layout(*cfg, lay);
+    if (rc) return rc;
+    TcPackTable tab;
+    tc_pack_table(*cfg, lay, tab);
+    dim3 grid(16, tab.n);
+    pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, (uint8_t*)packed, tab);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dtqn_tc_error(void) {
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
+    return v;
+}

@@ -1,0 +1,13 @@
+// Host-side interface of the tcgen05 Linear (linear_tc.cu).
+#pragma once
+#include "net.cuh"
+
+struct TcPackEntry { long long w_off, pk_off; int N, K, n_tile; };
+struct TcPackTable { TcPackEntry e[4 * DTQN_MAX_LAYERS + 1]; int n; long long total_bytes; };
+
+// entry order: per layer in_proj, out_proj, ffn.0, ffn.2; then the head's ffn.0
+enum { TC_W_IN = 0, TC_W_OUT = 1, TC_W_F1 = 2, TC_W_F2 = 3 };
+
+int tc_ntile(int N);
+int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab);
+int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st);

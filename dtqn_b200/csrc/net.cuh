@@ -89,3 +89,23 @@ static inline long long net_act_layout(const dtqn_net_cfg& c, long long T, int s
     A.total = o;
     return o;
 }
+
+// ---- shared by the CUDA-core and tcgen05 Linear kernels -----------------------------------------------------------------
+struct GroupPtrs { const float* p[DTQN_MAX_GROUPS]; };
+struct GroupSrc { dtqn_obs_src s[DTQN_MAX_GROUPS]; };
+
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_RES_LN = 2 };
+
+struct LinArgs {
+    const float* X;        // [G*Tg, K]
+    float* Y;              // [G*Tg, N]
+    GroupPtrs P;
+    long long w_off, b_off;
+    int Tg, N, K;
+    // EPI_RES_LN only (N == BN == d_model):
+    const float* R;        // residual input [G*Tg, N]
+    long long gamma_off, beta_off;
+    float* r_save;         // relu(a) [G*Tg, N]   (nullable)
+    float* st_save;        // (mean, rstd) [G*Tg, 2] (nullable)
+};
+

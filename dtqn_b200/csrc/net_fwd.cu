@@ -9,11 +9,10 @@
 #include "net.cuh"
 #include "gemm_simt.cuh"
 #include "prof.cuh"
+#include "linear_tc.cuh"
 
 namespace {
 
-struct GroupPtrs { const float* p[DTQN_MAX_GROUPS]; };
-struct GroupSrc { dtqn_obs_src s[DTQN_MAX_GROUPS]; };
 
 // ---- observation embedding + position ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -68,21 +67,6 @@ embed_kernel(GroupPtrs P, GroupSrc S, dtqn_net_cfg c, long long emb_table, long 
 }
 
 // ---- Linear with fused epilogues --------------------------------------------------------------------------------------
-enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_RES_LN = 2 };
-
-struct LinArgs {
-    const float* X;        // [G*Tg, K]
-    float* Y;              // [G*Tg, N]
-    GroupPtrs P;
-    long long w_off, b_off;
-    int Tg, N, K;
-    // EPI_RES_LN only (N == BN == d_model):
-    const float* R;        // residual input [G*Tg, N]
-    long long gamma_off, beta_off;
-    float* r_save;         // relu(a) [G*Tg, N]   (nullable)
-    float* st_save;        // (mean, rstd) [G*Tg, 2] (nullable)
-};
-
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 linear_kernel(LinArgs a) {
@@ -304,9 +288,13 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
     return net_act_layout(*cfg, n_tokens, save, nullptr, A);
 }
 
-extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const dtqn_obs_src* src,
-                            int32_t n_seq, int32_t L, int32_t q_mode, int32_t save, float* ws, int64_t ws_floats,
-                            float* q_out, void* stream) {
+// tokens per group from which the tcgen05 path (bf16x3 split, 128-row tiles) replaces the fp32 CUDA-core GEMMs
+static int g_tc_min_tokens = 4096;
+extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }
+
+extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const void* const* packed,
+                            const dtqn_obs_src* src, int32_t n_seq, int32_t L, int32_t q_mode, int32_t save, float* ws,
+                            int64_t ws_floats, float* q_out, void* stream) {
     if (!cfg || !params || !src || !ws || !q_out || G < 1 || G > DTQN_MAX_GROUPS || n_seq < 1 || L < 1) return DTQN_E_ARG;
     if (L > cfg->context_len) return DTQN_E_ARG;               // dtqn.py:171-173 assert
     NetLayout lay;
@@ -318,11 +306,22 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     cudaStream_t st = (cudaStream_t)stream;
     const int d = cfg->d_model, H = cfg->n_heads, hd = d / H;
     GroupPtrs P{}; GroupSrc S{};
+    const uint8_t* pk[DTQN_MAX_GROUPS] = {nullptr, nullptr, nullptr};
+    bool use_tc = packed != nullptr && Tg >= g_tc_min_tokens;
     for (int g = 0; g < G; ++g) {
         if (!params[g] || !src[g].obs) return DTQN_E_ARG;
         P.p[g] = params[g]; S.s[g] = src[g];
         if (src[g].timestep && src[g].ring_len < L) return DTQN_E_ARG;
+        if (packed) { pk[g] = (const uint8_t*)packed[g]; if (!pk[g]) use_tc = false; }
     }
+    TcPackTable tab{};
+    if (use_tc) tc_pack_table(*cfg, lay, tab);
+    auto linear = [&](const LinArgs& a, int epi, int tab_idx) -> int {
+        if (use_tc) return launch_linear_tc(a, epi, G, pk, tab.e[tab_idx].pk_off, st);
+        if (epi == EPI_BIAS) return launch_linear<EPI_BIAS>(a, G, d, st);
+        if (epi == EPI_BIAS_RELU) return launch_linear<EPI_BIAS_RELU>(a, G, d, st);
+        return launch_linear<EPI_RES_LN>(a, G, d, st);
+    };
     {
         dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
         prof_begin(PROF_EMBED, st);
@@ -339,7 +338,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.P = P; a.Tg = (int)Tg;
         // in_proj
         a.X = x_in; a.Y = la.qkv; a.w_off = lo.in_w; a.b_off = lo.in_b; a.N = 3 * d; a.K = d;
-        if ((rc = launch_linear<EPI_BIAS>(a, G, d, st))) return rc;
+        if ((rc = linear(a, EPI_BIAS, 4 * li + TC_W_IN))) return rc;
         // attention core
         {
             dim3 grid(H, (unsigned)(n_seq * G));
@@ -358,15 +357,15 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.X = la.o; a.Y = la.x1; a.w_off = lo.out_w; a.b_off = lo.out_b; a.N = d; a.K = d;
         a.R = x_in; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b;
         a.r_save = save ? la.r1 : nullptr; a.st_save = save ? la.st1 : nullptr;
-        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        if ((rc = linear(a, EPI_RES_LN, 4 * li + TC_W_OUT))) return rc;
         // ffn.0 + relu
         a.X = la.x1; a.Y = la.h; a.w_off = lo.f1_w; a.b_off = lo.f1_b; a.N = 4 * d; a.K = d;
-        if ((rc = launch_linear<EPI_BIAS_RELU>(a, G, d, st))) return rc;
+        if ((rc = linear(a, EPI_BIAS_RELU, 4 * li + TC_W_F1))) return rc;
         // ffn.2 -> relu -> +x1 -> LN2
         a.X = la.h; a.Y = la.x2; a.w_off = lo.f2_w; a.b_off = lo.f2_b; a.N = d; a.K = 4 * d;
         a.R = la.x1; a.gamma_off = lo.ln2_w; a.beta_off = lo.ln2_b;
         a.r_save = save ? la.r2 : nullptr; a.st_save = save ? la.st2 : nullptr;
-        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        if ((rc = linear(a, EPI_RES_LN, 4 * li + TC_W_F2))) return rc;
         x_in = la.x2;
     }
     // Q head

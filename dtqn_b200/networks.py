@@ -32,9 +32,15 @@ _l.dtqn_net_param_offsets.argtypes = [C.POINTER(NetCfg), C.POINTER(C.c_int64), C
 _l.dtqn_net_param_offsets.restype = C.c_int
 _l.dtqn_net_workspace_floats.argtypes = [C.POINTER(NetCfg), C.c_int64, C.c_int32]
 _l.dtqn_net_workspace_floats.restype = C.c_int64
-_l.dtqn_forward.argtypes = [C.POINTER(NetCfg), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(ObsSrc), C.c_int32, C.c_int32,
-                            C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+_l.dtqn_forward.argtypes = [C.POINTER(NetCfg), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(ObsSrc),
+                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
 _l.dtqn_forward.restype = C.c_int
+_l.dtqn_packed_bytes.argtypes = [C.POINTER(NetCfg)]
+_l.dtqn_packed_bytes.restype = C.c_int64
+_l.dtqn_pack_weights.argtypes = [C.POINTER(NetCfg), C.c_void_p, C.c_void_p, C.c_void_p]
+_l.dtqn_pack_weights.restype = C.c_int
+_l.dtqn_set_tc_min_tokens.argtypes = [C.c_int32]
+_l.dtqn_tc_error.restype = C.c_int
 
 
 class _Holder(nn.Module):
@@ -95,6 +101,20 @@ class DTQN(nn.Module):
         self._build_tree(dev)
         self._init_weights()
         self._ws = {}
+        # tcgen05 operand image of the GEMM weights (bf16 hi/lo, K-major tiles); refreshed by repack()
+        self.packed = torch.zeros(int(_l.dtqn_packed_bytes(C.byref(self.cfg))), dtype=torch.uint8, device=dev)
+        self.packed_stale = True
+
+    def repack(self) -> None:
+        """Refresh the tensor-core weight image from the fp32 parameters (after an optimiser step / load_state_dict)."""
+        _lib.check(_l.dtqn_pack_weights(C.byref(self.cfg), self.flat.data_ptr(), self.packed.data_ptr(),
+                                        _lib.stream_ptr()), "dtqn_pack_weights")
+        self.packed_stale = False
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.packed_stale = True
+        return out
 
     # ---- parameter tree -----------------------------------------------------------------------------------------------
     def _view(self, shape, trainable=True):
@@ -194,17 +214,31 @@ class DTQN(nn.Module):
         x = obss.to(device=self.flat.device, dtype=torch.float32).contiguous()
         q = torch.empty((B, L, self.num_actions), dtype=torch.float32, device=self.flat.device)
         src = ObsSrc(obs=x.data_ptr(), seq_stride=L * O, timestep=None, ring_len=0, _pad=0)
-        forward_groups(self, [self.flat], [src], B, L, q_mode=0, save=0, q_out=q)
+        forward_groups(self, [self], [src], B, L, q_mode=0, save=0, q_out=q)
         return q
 
 
-def forward_groups(net: DTQN, flats, srcs, n_seq: int, L: int, q_mode: int, save: int, q_out: torch.Tensor,
+def forward_groups(net: DTQN, nets, srcs, n_seq: int, L: int, q_mode: int, save: int, q_out: torch.Tensor,
                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dtqn_forward over len(flats) groups sharing one launch sequence.  Returns the workspace used."""
-    G = len(flats)
+    """dtqn_forward over len(nets) groups (group g uses nets[g]'s parameters) sharing one launch sequence.
+    Returns the workspace used."""
+    G = len(nets)
     ws = workspace if workspace is not None else net.workspace(G * n_seq * L, save)
-    pp = (C.c_void_p * G)(*[f.data_ptr() for f in flats])
+    for m in nets:
+        if m.packed_stale:
+            m.repack()
+    pp = (C.c_void_p * G)(*[m.flat.data_ptr() for m in nets])
+    pk = (C.c_void_p * G)(*[m.packed.data_ptr() for m in nets])
     ss = (ObsSrc * G)(*srcs)
-    _lib.check(_l.dtqn_forward(C.byref(net.cfg), G, pp, ss, n_seq, L, q_mode, save, ws.data_ptr(), ws.numel(),
+    _lib.check(_l.dtqn_forward(C.byref(net.cfg), G, pp, pk, ss, n_seq, L, q_mode, save, ws.data_ptr(), ws.numel(),
                                q_out.data_ptr(), _lib.stream_ptr()), "dtqn_forward")
     return ws
+
+
+def set_tc_min_tokens(n: int) -> None:
+    """Groups with >= n tokens run their GEMMs on the tcgen05 path (default 4096)."""
+    _l.dtqn_set_tc_min_tokens(int(n))
+
+
+def tc_error() -> bool:
+    return bool(_l.dtqn_tc_error())

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DTQN_ABI_VERSION 1
+#define DTQN_ABI_VERSION 2
 
 #define DTQN_E_ARG      (-1)  /* null pointer / out-of-range size */
 #define DTQN_E_UNSUPPORTED (-2)
@@ -172,9 +172,20 @@ int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_tokens, int
  *   q_mode 0: q_out[g, i, j, :] for every position (training, dtqn/agents/dtqn.py:215-233);
  *   q_mode 1: q_out[g, i, :] = Q at the last valid position n_i - 1 (acting, dtqn/agents/dtqn.py:101-107).
  * save = 1 keeps every layer's activations in `workspace` for dtqn_td_backward. */
-int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* params, const dtqn_obs_src* src,
-                 int32_t n_seq, int32_t seq_len, int32_t q_mode, int32_t save, float* workspace,
+int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* params,
+                 const void* const* packed /* nullable: per-group dtqn_pack_weights images -> tcgen05 GEMMs */,
+                 const dtqn_obs_src* src, int32_t n_seq, int32_t seq_len, int32_t q_mode, int32_t save, float* workspace,
                  int64_t workspace_floats, float* q_out, void* stream);
+
+/* tcgen05 operand images of the GEMM weights (in_proj / out_proj / ffn.0 / ffn.2 per layer + head ffn.0): each weight
+ * split into bf16 hi + lo and tiled in the K-major shared-memory layout the tensor core reads, so the kernel fetches a
+ * [N_TILE x 64] block with one TMA bulk copy.  Re-pack after every optimiser step / target update. */
+int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg);
+int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed, void* stream);
+/* Groups with at least this many tokens use the tcgen05 path (default 4096); smaller ones stay on fp32 CUDA cores. */
+int dtqn_set_tc_min_tokens(int32_t n_tokens);
+/* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
+int dtqn_tc_error(void);
 
 /* Double-DQN sequence TD loss + backward (dtqn/agents/dtqn.py:215-256) for a forward made with n_groups = 3,
  * save = 1, q_mode = 0 over (policy|obs, policy|next_obs, target|next_obs).  Zeroes `grads` (flat, same layout as

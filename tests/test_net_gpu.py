@@ -132,3 +132,35 @@ def test_acting_forward_from_context_ring(golden_dir):
     ref = z["greedy_q"][steps]
     assert rel_err(q, ref) < Q_REL_TIGHT
     assert np.array_equal(q.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("env", ["carflag", "memory"])
+def test_tcgen05_forward_vs_oracle(golden_dir, env):
+    """Large-M forward on the tcgen05 path (bf16 hi/lo split, 3 MMAs per k-step) against the fp32 CPU oracle on the same
+    weights and inputs: Q within the 1e-3 north-star bar (and the CUDA-core path within 2e-5 on the same batch)."""
+    from dtqn_b200 import networks
+    from oracle import network as onet
+    z = np.load(os.path.join(golden_dir, f"forward_{env}.npz"))
+    net = _make_net(z, "policy/", env)
+    sd = {k: v.float() for k, v in _sd(z, "policy/").items()}
+    ctx = int(z["meta"][2])
+    g = torch.Generator().manual_seed(0)
+    n_seq = 131                                                  # 6550 tokens: tail tile + >= 4096 -> tensor-core path
+    if env == "carflag":
+        x = torch.empty(n_seq, ctx, 3).uniform_(-1.1, 1.1, generator=g)
+        x[:, :, 2] = torch.randint(-1, 2, (n_seq, ctx), generator=g).float()
+    else:
+        x = torch.randint(0, 9, (n_seq, ctx, 10), generator=g)
+    with torch.no_grad():
+        ref = onet.forward(sd, x, 8).numpy()
+    networks.set_tc_min_tokens(1 << 30)
+    q_simt = net(x).cpu().numpy()
+    networks.set_tc_min_tokens(4096)
+    q_tc = net(x).cpu().numpy()
+    torch.cuda.synchronize()
+    assert not networks.tc_error(), "a tcgen05 kernel timed out on an mbarrier"
+    e_simt, e_tc = rel_err(q_simt, ref), rel_err(q_tc, ref)
+    print(f"{env}: rel err cuda-core {e_simt:.3e}  tcgen05 {e_tc:.3e}")
+    assert e_simt < Q_REL_TIGHT
+    assert e_tc < Q_REL_TOL, e_tc
+    assert e_tc < 2e-4, e_tc        # expected for the bf16x3 split
