@@ -333,6 +333,10 @@ int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab)
         add(l.in_w, 3 * d, d); add(l.out_w, d, d); add(l.f1_w, 4 * d, d); add(l.f2_w, d, 4 * d);
     }
     add(lay.h1_w, d, d);
+    for (int i = 0; i < c.n_layers; ++i) {                      // acting: K|V rows and Q rows of in_proj as separate operands
+        add(lay.layer[i].in_w + (long long)d * d, 2 * d, d);
+        add(lay.layer[i].in_w, d, d);
+    }
     tab.n = n; tab.total_bytes = off;
     return 0;
 }

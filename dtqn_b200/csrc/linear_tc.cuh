@@ -3,9 +3,10 @@
 #include "net.cuh"
 
 struct TcPackEntry { long long w_off, pk_off; int N, K, n_tile; };
-struct TcPackTable { TcPackEntry e[4 * DTQN_MAX_LAYERS + 1]; int n; long long total_bytes; };
+struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1]; int n; long long total_bytes; };
 
-// entry order: per layer in_proj, out_proj, ffn.0, ffn.2; then the head's ffn.0
+// entry order: per layer in_proj, out_proj, ffn.0, ffn.2; then the head's ffn.0; then per layer the K|V rows and the Q rows
+// of in_proj (index 4*n_layers + 1 + 2*i, + 1)
 enum { TC_W_IN = 0, TC_W_OUT = 1, TC_W_F1 = 2, TC_W_F2 = 3 };
 
 int tc_ntile(int N);

@@ -139,7 +139,7 @@ dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const fl
 
 // ---- wgrad:  gW[Nf, Kf] += dY[T, Nf]^T X[T, Kf];  gb[Nf] += colsum(dY) --------------------------------------------------------
 // 64 x 64 tile of gW per CTA, tokens split over gridDim.z chunks, fp32 atomics into the (zeroed) flat gradient.
-#define WG_CHUNK 256
+#define WG_CHUNK 64
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int Nf, int Kf,
              float* __restrict__ gW, float* __restrict__ gb) {

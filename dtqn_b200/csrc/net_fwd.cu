@@ -203,6 +203,66 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
         *reinterpret_cast<float4*>(op + c4) = make_float4(accv[c4] * inv, accv[c4 + 1] * inv, accv[c4 + 2] * inv, accv[c4 + 3] * inv);
 }
 
+
+// ---- acting: attention of the LAST valid query only (the policy reads q[:, -1, :], agents/dtqn.py:107) ------------------
+// ql [G*n_seq, d] = scaled-later query of the last valid token; kv [T, 2d] = (k | v) of every token.  One warp per
+// (sequence, head): lanes stride over the n_i keys, warp-shuffle softmax, then HD warp reductions for P V.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_last_kernel(const float* __restrict__ ql, const float* __restrict__ kv, GroupSrc S, int n_seq, int L, int d,
+                 float scale, float* __restrict__ ol) {
+    const int g = blockIdx.y, i = blockIdx.x;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const dtqn_obs_src& s = S.s[g];
+    int n = L;
+    if (s.timestep) n = min(min(s.ring_len, s.timestep[i] + 1), L);
+    const size_t seq = (size_t)g * n_seq + i;
+    const float* qp = ql + seq * d + h * HD;
+    float q[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) q[c] = qp[c] * scale;
+    const float* kbase = kv + seq * L * (size_t)(2 * d) + h * HD;
+    float sc[4];                                               // up to 128 keys: 4 per lane
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int j = lane + 32 * r;
+        sc[r] = -INFINITY;
+        if (j < n) {
+            const float* kp = kbase + (size_t)j * (2 * d);
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) a = fmaf(q[c], kp[c], a);
+            sc[r] = a;
+        }
+        m = fmaxf(m, sc[r]);
+    }
+    m = warp_max(m);
+    float l = 0.f, acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int j = lane + 32 * r;
+        if (j < n) {
+            const float pw = expf(sc[r] - m);
+            l += pw;
+            const float* vp = kbase + (size_t)j * (2 * d) + d;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) acc[c] = fmaf(pw, vp[c], acc[c]);
+        }
+    }
+    l = warp_sum(l);
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+        const float inv = 1.f / l;
+        float* op = ol + seq * d + h * HD;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) op[c] = acc[c] * inv;
+    }
+}
+
 // ---- rows of the last valid position of every sequence (acting: q[:, -1, :], agents/dtqn.py:107) ---------------------
 __global__ void gather_last_kernel(const float* __restrict__ x, GroupSrc S, int n_seq, int L, int d, float* __restrict__ out) {
     const int g = blockIdx.z;
@@ -331,7 +391,11 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         DTQN_LAUNCH_CHECK();
     }
     const float* x_in = act.x0;
-    for (int li = 0; li < cfg->n_layers; ++li) {
+    // acting (q_mode 1) needs the final layer's output at ONE position per sequence: that layer only projects K/V for
+    // every token; its query, attention row, out_proj, FFN and LayerNorms run on n_seq rows (exactly the same values).
+    const bool last_only = q_mode == 1 && L >= 3 && H * 32 <= 256;
+    const int n_full = last_only ? cfg->n_layers - 1 : cfg->n_layers;
+    for (int li = 0; li < n_full; ++li) {
         const LayerOff& lo = lay.layer[li];
         const LayerAct& la = act.layer[li];
         LinArgs a{};
@@ -371,7 +435,50 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     // Q head
     long long Th = Tg;
     const float* head_in = x_in;
-    if (q_mode == 1) {
+    if (last_only) {
+        const int li = cfg->n_layers - 1;
+        const LayerOff& lo = lay.layer[li];
+        const LayerAct& la = act.layer[li];
+        const long long nd = (long long)G * n_seq * d;
+        float* xl = la.h;                 // [G*n_seq, d] carved out of the (T x 4d) FFN buffer: 9*n_seq*d <= n_seq*L*4d
+        float* qlb = xl + nd; float* olb = qlb + nd; float* x1l = olb + nd; float* hl = x1l + nd; float* x2l = hl + 4 * nd;
+        {
+            dim3 grid(dtqn_cdiv((long long)n_seq * d, 256), 1, G);
+            prof_begin(PROF_OTHER, st);
+            gather_last_kernel<<<grid, 256, 0, st>>>(x_in, S, n_seq, L, d, xl);
+            prof_end(PROF_OTHER, st, 0.0);
+            DTQN_LAUNCH_CHECK();
+        }
+        LinArgs a{};
+        a.P = P;
+        // K | V of every token: rows [d, 3d) of in_proj
+        a.Tg = (int)Tg; a.X = x_in; a.Y = la.qkv; a.w_off = lo.in_w + (long long)d * d; a.b_off = lo.in_b + d; a.N = 2 * d; a.K = d;
+        if ((rc = linear(a, EPI_BIAS, 4 * cfg->n_layers + 1 + 2 * li))) return rc;
+        // Q of the last token: rows [0, d)
+        a.Tg = n_seq; a.X = xl; a.Y = qlb; a.w_off = lo.in_w; a.b_off = lo.in_b; a.N = d; a.K = d;
+        if ((rc = launch_linear<EPI_BIAS>(a, G, d, st))) return rc;
+        {
+            dim3 grid(n_seq, G);
+            const float scale = 1.0f / sqrtf((float)hd);
+            prof_begin(PROF_ATTN_FWD, st);
+            if (hd == 8) attn_last_kernel<8><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 16) attn_last_kernel<16><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 32) attn_last_kernel<32><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 4) attn_last_kernel<4><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else return DTQN_E_UNSUPPORTED;
+            prof_end(PROF_ATTN_FWD, st, 4.0 * (double)G * n_seq * L * d);
+            DTQN_LAUNCH_CHECK();
+        }
+        a.X = olb; a.Y = x1l; a.w_off = lo.out_w; a.b_off = lo.out_b; a.N = d; a.K = d;
+        a.R = xl; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b; a.r_save = nullptr; a.st_save = nullptr;
+        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        a.X = x1l; a.Y = hl; a.w_off = lo.f1_w; a.b_off = lo.f1_b; a.N = 4 * d; a.K = d;
+        if ((rc = launch_linear<EPI_BIAS_RELU>(a, G, d, st))) return rc;
+        a.X = hl; a.Y = x2l; a.w_off = lo.f2_w; a.b_off = lo.f2_b; a.N = d; a.K = 4 * d;
+        a.R = x1l; a.gamma_off = lo.ln2_w; a.beta_off = lo.ln2_b;
+        if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;
+        head_in = x2l; Th = n_seq;
+    } else if (q_mode == 1) {
         // only the last valid position feeds the head; qkv of layer 0 is free scratch by now
         float* xl = act.layer[0].qkv;
         dim3 grid(dtqn_cdiv((long long)n_seq * d, 256), 1, G);
