@@ -19,6 +19,7 @@ from dtqn_b200 import _lib
 from dtqn_b200.buffers import ReplayBuffer
 from dtqn_b200.envs import ContextWindow
 from dtqn_b200.networks import DTQN, NetCfg, ObsSrc, forward_groups
+from dtqn_b200.parallel import allreduce_gradients
 
 _l = _lib.lib
 _l.dtqn_td_scratch_floats.argtypes = [C.POINTER(NetCfg), C.c_int32, C.c_int32]
@@ -174,11 +175,9 @@ class DtqnAgent:
         """Gradient allreduce (the one collective, only when world > 1) -> /world -> global-norm clip -> Adam, identical
         on every rank."""
         net, st = self.policy_network, _lib.stream_ptr()
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(self.grads)                      # sum of per-rank mean-MSE gradients
+        scale = allreduce_gradients(self.grads)              # sum of per-rank mean-MSE gradients; scale = 1/world
         _lib.check(_l.dtqn_clip_adam(net.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
-                                     self.exp_avg_sq.data_ptr(), net.n_flat, 1.0 / world, self.grad_norm_clip,
+                                     self.exp_avg_sq.data_ptr(), net.n_flat, scale, self.grad_norm_clip,
                                      self.learning_rate, self.betas[0], self.betas[1], self.adam_eps,
                                      self.opt_step.data_ptr(), self.opt_scratch.data_ptr(), self.stats.data_ptr(),
                                      self.flags.data_ptr(), self.stats_ring.data_ptr(), RING, st), "dtqn_clip_adam")

@@ -8,18 +8,9 @@ import torch.distributed as dist
 
 from dtqn_b200 import _lib
 from dtqn_b200.envs import BatchedEnv
+from dtqn_b200.parallel import broadcast_parameters, rank_world, shard_seed
 from dtqn_b200.utils import LinearAnneal, get_agent
 
-
-def rank_world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
-
-
-def shard_seed(seed: int, rank: int, n_envs: int) -> int:
-    """Rank g owns env seeds [seed + g*n_envs, seed + (g+1)*n_envs)."""
-    return seed + rank * n_envs
 
 
 class BatchedTrainer:
@@ -41,7 +32,8 @@ class BatchedTrainer:
                                E, history or context, tuf, gamma, num_heads=heads, num_layers=layers, n_envs=n_envs,
                                trunc_context_obs=trunc_context_obs, sample_seed=seed * 7919 + rank)
         if world > 1:
-            dist.broadcast(self.agent.policy_network.flat, src=0)
+            broadcast_parameters(self.agent.policy_network.flat, src=0)
+            self.agent.policy_network.packed_stale = True
             self.agent.target_update()
         self.env.attach(self.agent.replay_buffer, self.agent.train_context)
         self.eps = LinearAnneal(1.0, 0.1, max(1, num_steps // 10))     # run.py:420
