@@ -310,7 +310,289 @@ int launch_one(const TcArgs& t, int G, cudaStream_t st) {
     return 0;
 }
 
+
+// =================================================================================================================================
+// Pipelined persistent variant (the one the acting forward runs): weights resident in shared memory for the CTA's whole
+// life, warp-specialised roles connected by mbarriers, two shared-memory stages for the activation operand and two TMEM
+// accumulators, so the global loads of tile i+1, the MMAs of tile i and the epilogue / stores of tile i-1 overlap:
+//   warps 0-7  (256 thr)  producers: fp32 activations (coalesced) -> bf16 hi/lo -> canonical K-major smem stage
+//   warp  8               one elected thread: TMA bulk load of the weight image (once), tcgen05.mma issue, tcgen05.commit
+//   warps 9-12 (128 thr)  epilogue: tcgen05.ld (thread = row) -> bias / ReLU / residual+LayerNorm -> padded smem staging ->
+//                          one TMA bulk store per row segment (cp.async.bulk.global.shared::cta), double buffered
+// =================================================================================================================================
+constexpr int PIPE_PRODUCERS = 256;
+constexpr int PIPE_THREADS = PIPE_PRODUCERS + 32 + 128;
+constexpr int STG_COLS = 64;                                   // columns staged per epilogue round
+constexpr int STG_ROW_BYTES = STG_COLS * 4 + 16;               // padded row -> conflict-free 16-byte stores
+constexpr int STG_BYTES = TC_M * STG_ROW_BYTES;
+constexpr int A_STAGE_BYTES = (2 * A_HALF_BYTES + 1023) & ~1023;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <int N_TILE, int K_CHUNKS, int EPI>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+linear_tc_pipe_kernel(TcArgs t) {
+    extern __shared__ uint8_t smem_raw[];
+    const LinArgs& a = t.a;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NT_PER_G_DUMMY = 0; (void)NT_PER_G_DUMMY;
+    const int n_ntiles = a.N / N_TILE;
+    const int g = blockIdx.y / n_ntiles, nt = blockIdx.y % n_ntiles;
+    constexpr int TMEM_COLS = (2 * N_TILE) <= 128 ? 128 : ((2 * N_TILE) <= 256 ? 256 : 512);
+    constexpr uint32_t B_HALF = N_TILE * TC_KC * 2;            // one of hi / lo of one k-chunk block
+    constexpr uint32_t B_BYTES = 2 * B_HALF * K_CHUNKS;
+
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = base;                                        // resident weight image: K_CHUNKS x {hi, lo}
+    uint8_t* sA = sB + ((B_BYTES + 1023) & ~1023u);            // 2 stages
+    uint8_t* sStg = sA + 2 * A_STAGE_BYTES;                    // 2 staging buffers
+    float* sBias = reinterpret_cast<float*>(sStg + 2 * STG_BYTES);       // bias | gamma | beta, N_TILE each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 3 * N_TILE);    // a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    enum { A_FULL = 0, A_EMPTY = 2, ACC_FULL = 4, ACC_EMPTY = 6, B_FULL = 8 };
+
+    const float* p = a.P.p[g];
+    if (tid < N_TILE) {
+        sBias[tid] = __ldg(p + a.b_off + nt * N_TILE + tid);
+        if (EPI == EPI_RES_LN) {
+            sBias[N_TILE + tid] = __ldg(p + a.gamma_off + tid);
+            sBias[2 * N_TILE + tid] = __ldg(p + a.beta_off + tid);
+        }
+    }
+    if (tid == 0) {
+        mbar_init(BAR(A_FULL), PIPE_PRODUCERS); mbar_init(BAR(A_FULL + 1), PIPE_PRODUCERS);
+        mbar_init(BAR(A_EMPTY), 1); mbar_init(BAR(A_EMPTY + 1), 1);
+        mbar_init(BAR(ACC_FULL), 1); mbar_init(BAR(ACC_FULL + 1), 1);
+        mbar_init(BAR(ACC_EMPTY), 128); mbar_init(BAR(ACC_EMPTY + 1), 128);
+        mbar_init(BAR(B_FULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    const size_t grow = (size_t)g * a.Tg;
+    const int m_tiles = (a.Tg + TC_M - 1) / TC_M;
+    const int my_tiles = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
+
+    if (warp < 8) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        const float* X = a.X + grow * a.K;
+        int it = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
+            for (int kc = 0; kc < K_CHUNKS; ++kc, ++it) {
+                const int st = it & 1;
+                if (it >= 2 && !mbar_wait(BAR(A_EMPTY + st), (uint32_t)(((it >> 1) - 1) & 1))) return;
+                uint8_t* dst = sA + st * A_STAGE_BYTES;
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                  // 32 rows x 64 floats per pass; a warp reads 4 rows x 256 B
+                    const int r = q * 32 + (tid >> 3), c = tid & 7;
+                    if (m0 + r < a.Tg) {
+                        const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + kc * TC_KC + c * 8);
+                        v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
+                    } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = q * 32 + (tid >> 3), c = tid & 7;
+                    const float x[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    *reinterpret_cast<uint4*>(dst + c * A_CHUNK_STRIDE + r * 16) = hi;
+                    *reinterpret_cast<uint4*>(dst + A_HALF_BYTES + c * A_CHUNK_STRIDE + r * 16) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(BAR(A_FULL + st));
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0) {
+            const uint8_t* wimg = t.packed[g] + t.pk_off + (size_t)nt * B_BYTES;
+            mbar_expect_tx(BAR(B_FULL), B_BYTES);
+#pragma unroll 1
+            for (uint32_t off = 0; off < B_BYTES; off += 32768u)
+                bulk_g2s(smem_u32(sB) + off, wimg + off, (B_BYTES - off) < 32768u ? (B_BYTES - off) : 32768u, BAR(B_FULL));
+            bool ok = mbar_wait(BAR(B_FULL), 0);
+            const uint32_t idesc = umma_idesc(TC_M, N_TILE);
+            const uint32_t sB_u = smem_u32(sB);
+            int it = 0;
+            for (int i = 0; i < my_tiles && ok; ++i) {
+                const int as = i & 1;
+                if (i >= 2) ok = mbar_wait(BAR(ACC_EMPTY + as), (uint32_t)(((i >> 1) - 1) & 1));
+                const uint32_t d_tmem = tmem + (uint32_t)(as * N_TILE);
+                for (int kc = 0; kc < K_CHUNKS && ok; ++kc, ++it) {
+                    const int st = it & 1;
+                    ok = mbar_wait(BAR(A_FULL + st), (uint32_t)((it >> 1) & 1));
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t sA_u = smem_u32(sA + st * A_STAGE_BYTES);
+                    const uint32_t sBk = sB_u + (uint32_t)kc * 2u * B_HALF;
+#pragma unroll
+                    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+                        const uint64_t a_hi = umma_desc(sA_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t a_lo = umma_desc(sA_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t b_hi = umma_desc(sBk + k16 * 2 * (N_TILE * 16), N_TILE * 16, 128);
+                        const uint64_t b_lo = umma_desc(sBk + B_HALF + k16 * 2 * (N_TILE * 16), N_TILE * 16, 128);
+                        umma_bf16(d_tmem, a_hi, b_hi, idesc, (kc | k16) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                    }
+                    umma_commit(BAR(A_EMPTY + st));            // smem stage reusable once these MMAs retire
+                }
+                if (ok) umma_commit(BAR(ACC_FULL + as));       // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue ------------------------------------------------
+        const int q4 = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row_in_tile = q4 * 32 + lane;
+        const int n0 = nt * N_TILE;
+        int round = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int as = i & 1;
+            const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
+            if (!mbar_wait(BAR(ACC_FULL + as), (uint32_t)((i >> 1) & 1))) break;
+            tc_fence_after();
+            const int r = m0 + row_in_tile;
+            const bool row_ok = r < a.Tg;
+            const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * N_TILE);
+            if (EPI != EPI_RES_LN) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
+                    uint8_t* stg = sStg + (round & 1) * STG_BYTES + row_in_tile * STG_ROW_BYTES;
+                    bulk_wait_read<1>();                        // the buffer written two rounds ago has been read out
+#pragma unroll
+                    for (int cc = 0; cc < STG_COLS; cc += 16) {
+                        float v[16];
+                        tmem_ld16(trow + c0 + cc, v);
+#pragma unroll
+                        for (int q = 0; q < 16; q += 4) {
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                o[e] = v[q + e] + sBias[c0 + cc + q + e];
+                                if (EPI == EPI_BIAS_RELU) o[e] = fmaxf(o[e], 0.f);
+                            }
+                            *reinterpret_cast<float4*>(stg + (cc + q) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    fence_async_smem();
+                    if (row_ok) bulk_s2g(a.Y + (grow + r) * (size_t)a.N + n0 + c0, smem_u32(stg), STG_COLS * 4);
+                    bulk_commit();
+                }
+            } else {
+                // x_out = LayerNorm(x_res + relu(acc + b)); N_TILE == d_model, the row lives in this thread
+                float u[N_TILE];
+                const size_t ro = (grow + (row_ok ? r : 0)) * (size_t)N_TILE;
+                float s = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c0, v);
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        const float4 xr = *reinterpret_cast<const float4*>(a.R + ro + c0 + q);
+                        const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            u[c0 + q + e] = xv[e] + fmaxf(v[q + e] + sBias[c0 + q + e], 0.f);
+                            s += u[c0 + q + e];
+                        }
+                    }
+                }
+                const float mean = s * (1.f / N_TILE);
+                float vs = 0.f;
+#pragma unroll
+                for (int j = 0; j < N_TILE; ++j) { const float dl = u[j] - mean; vs = fmaf(dl, dl, vs); }
+                const float rstd = 1.0f / sqrtf(vs * (1.f / N_TILE) + 1e-5f);
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
+                    uint8_t* stg = sStg + (round & 1) * STG_BYTES + row_in_tile * STG_ROW_BYTES;
+                    bulk_wait_read<1>();
+#pragma unroll
+                    for (int q = 0; q < STG_COLS; q += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = (u[c0 + q + e] - mean) * rstd * sBias[N_TILE + c0 + q + e] + sBias[2 * N_TILE + c0 + q + e];
+                        *reinterpret_cast<float4*>(stg + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                    fence_async_smem();
+                    if (row_ok) bulk_s2g(a.Y + ro + c0, smem_u32(stg), STG_COLS * 4);
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC_EMPTY + as));                   // accumulator stage drained
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all row stores complete before smem goes away
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+template <int N_TILE, int K_CHUNKS, int EPI>
+int launch_pipe(const TcArgs& t, int G, cudaStream_t st) {
+    constexpr size_t B_BYTES = (size_t)N_TILE * TC_KC * 4 * K_CHUNKS;
+    constexpr size_t smem = 1024 + ((B_BYTES + 1023) & ~(size_t)1023) + 2 * A_STAGE_BYTES + 2 * STG_BYTES + 3 * N_TILE * 4 + 128;
+    static_assert(smem <= 227 * 1024, "pipelined tcgen05 Linear: shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tc_pipe_kernel<N_TILE, K_CHUNKS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int m_tiles = dtqn_cdiv(t.a.Tg, TC_M);
+    const int gy = (t.a.N / N_TILE) * G;
+    int gx = 148 / gy; if (gx < 1) gx = 1; if (gx > m_tiles) gx = m_tiles;
+    linear_tc_pipe_kernel<N_TILE, K_CHUNKS, EPI><<<dim3(gx, gy, 1), PIPE_THREADS, smem, st>>>(t);
+    return 0;
+}
+
+// shapes whose whole [N_TILE x K] hi+lo weight image fits beside the pipeline buffers (<= 64 KB)
+template <int EPI>
+int launch_pipe_dispatch(const TcArgs& t, int G, int nt, cudaStream_t st, bool& handled) {
+    handled = true;
+    const int K = t.a.K;
+    if constexpr (EPI == EPI_RES_LN) {
+        if (t.a.N == 64 && K == 64) return launch_pipe<64, 1, EPI>(t, G, st);
+        if (t.a.N == 64 && K == 256) return launch_pipe<64, 4, EPI>(t, G, st);
+        if (t.a.N == 128 && K == 128) return launch_pipe<128, 2, EPI>(t, G, st);
+    } else {
+        if (nt == 64 && K == 64) return launch_pipe<64, 1, EPI>(t, G, st);
+        if (nt == 128 && K == 64) return launch_pipe<128, 1, EPI>(t, G, st);
+        if (nt == 192 && K == 64) return launch_pipe<192, 1, EPI>(t, G, st);
+        if (nt == 256 && K == 64) return launch_pipe<256, 1, EPI>(t, G, st);
+        if (nt == 128 && K == 128) return launch_pipe<128, 2, EPI>(t, G, st);
+    }
+    handled = false;
+    return 0;
+}
+
 }  // namespace
+
+static int g_tc_pipelined = 1;
+extern "C" int dtqn_set_tc_pipelined(int32_t on) { g_tc_pipelined = on; return 0; }
 
 int tc_ntile(int N) {
     switch (N) {
@@ -349,6 +631,18 @@ int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* pac
     if (!nt || a.K % TC_KC) return DTQN_E_UNSUPPORTED;
     int rc = DTQN_E_UNSUPPORTED;
     prof_begin(PROF_LINEAR, st);
+    bool handled = false;
+    if (g_tc_pipelined) {
+        if (epi == EPI_RES_LN) rc = launch_pipe_dispatch<EPI_RES_LN>(t, G, nt, st, handled);
+        else if (epi == EPI_BIAS) rc = launch_pipe_dispatch<EPI_BIAS>(t, G, nt, st, handled);
+        else rc = launch_pipe_dispatch<EPI_BIAS_RELU>(t, G, nt, st, handled);
+    }
+    if (handled) {
+        prof_end(PROF_LINEAR, st, 2.0 * (double)a.Tg * G * a.N * a.K);
+        if (rc) return rc;
+        DTQN_LAUNCH_CHECK();
+        return 0;
+    }
     if (epi == EPI_RES_LN) {
         if (a.N == 64) rc = launch_one<64, EPI_RES_LN>(t, G, st);
         else if (a.N == 128) rc = launch_one<128, EPI_RES_LN>(t, G, st);

@@ -204,6 +204,116 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
 }
 
 
+
+// ---- causal self-attention, one CTA per sequence (all heads) ----------------------------------------------------------------
+// K and V of the whole sequence are staged once in shared memory with coalesced loads; warp h = head h.  Lane r owns the
+// query rows r and L-1-r (balanced causal work), keys are visited in warp-uniform blocks of 4 so every K / V read is a
+// broadcast float4 shared by both rows, with one rescale of the online softmax per block.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int d, float scale) {
+    extern __shared__ float sm_kv[];
+    float* Ks = sm_kv;
+    float* Vs = sm_kv + (size_t)L * d;
+    const size_t t0 = (size_t)blockIdx.x * L;
+    const int tid = threadIdx.x, dq = d / 4;
+    for (int e = tid; e < L * dq; e += blockDim.x) {
+        const int r = e / dq, c4 = (e % dq) * 4;
+        const float* base = qkv + (t0 + r) * (size_t)(3 * d) + c4;
+        *reinterpret_cast<float4*>(Ks + (size_t)r * d + c4) = *reinterpret_cast<const float4*>(base + d);
+        *reinterpret_cast<float4*>(Vs + (size_t)r * d + c4) = *reinterpret_cast<const float4*>(base + 2 * d);
+    }
+    __syncthreads();
+    const int h = tid >> 5, lane = tid & 31;
+    const int half = (L + 1) / 2;
+    for (int r0 = 0; r0 < half; r0 += 32) {                  // L <= 64: one pass; L = 128: two
+        const int r = r0 + lane;
+        const bool act = r < half;
+        const int ra = act ? r : 0, rb = act ? L - 1 - r : 0;
+        const bool two = act && (rb != ra);
+        float qa[HD], qb[HD], aa[HD], ab[HD];
+        {
+            const float* pa = qkv + (t0 + ra) * (size_t)(3 * d) + h * HD;
+            const float* pb = qkv + (t0 + rb) * (size_t)(3 * d) + h * HD;
+#pragma unroll
+            for (int c = 0; c < HD; c += 4) {
+                const float4 va = *reinterpret_cast<const float4*>(pa + c), vb = *reinterpret_cast<const float4*>(pb + c);
+                qa[c] = va.x * scale; qa[c + 1] = va.y * scale; qa[c + 2] = va.z * scale; qa[c + 3] = va.w * scale;
+                qb[c] = vb.x * scale; qb[c + 1] = vb.y * scale; qb[c + 2] = vb.z * scale; qb[c + 3] = vb.w * scale;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < HD; ++c) { aa[c] = 0.f; ab[c] = 0.f; }
+        float ma = -INFINITY, la_ = 0.f, mb = -INFINITY, lb = 0.f;
+        const int last_a = min(half, r0 + 32) - 1;            // largest "a" row handled by this warp pass (warp-uniform)
+        for (int j0 = 0; j0 < L; j0 += 4) {
+            const bool do_a = j0 <= last_a;                   // warp-uniform: the upper half of the keys only feeds rows b
+            float sa[4], sb[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = min(j0 + jj, L - 1);
+                const float* kp = Ks + (size_t)j * d + h * HD;
+                float da = 0.f, db = 0.f;
+#pragma unroll
+                for (int c = 0; c < HD; c += 4) {
+                    const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+                    db = fmaf(qb[c], kv.x, db); db = fmaf(qb[c + 1], kv.y, db); db = fmaf(qb[c + 2], kv.z, db); db = fmaf(qb[c + 3], kv.w, db);
+                    if (do_a) { da = fmaf(qa[c], kv.x, da); da = fmaf(qa[c + 1], kv.y, da); da = fmaf(qa[c + 2], kv.z, da); da = fmaf(qa[c + 3], kv.w, da); }
+                }
+                sa[jj] = (j0 + jj <= ra) ? da : -INFINITY;    // causal mask (additive -inf above the diagonal)
+                sb[jj] = (j0 + jj <= rb) ? db : -INFINITY;
+            }
+            const float nmb = fmaxf(mb, fmaxf(fmaxf(sb[0], sb[1]), fmaxf(sb[2], sb[3])));
+            const float cb = expf(mb - nmb);
+            float pb_[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) pb_[jj] = expf(sb[jj] - nmb);
+            lb = lb * cb + (pb_[0] + pb_[1]) + (pb_[2] + pb_[3]);
+            mb = nmb;
+            float ca = 1.f, pa_[4] = {0.f, 0.f, 0.f, 0.f};
+            if (do_a) {
+                const float nma = fmaxf(ma, fmaxf(fmaxf(sa[0], sa[1]), fmaxf(sa[2], sa[3])));
+                ca = expf(ma - nma);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) pa_[jj] = expf(sa[jj] - nma);
+                la_ = la_ * ca + (pa_[0] + pa_[1]) + (pa_[2] + pa_[3]);
+                ma = nma;
+            }
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { ab[c] *= cb; if (do_a) aa[c] *= ca; }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = min(j0 + jj, L - 1);
+                const float* vp = Vs + (size_t)j * d + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD; c += 4) {
+                    const float4 vv = *reinterpret_cast<const float4*>(vp + c);
+                    ab[c] = fmaf(pb_[jj], vv.x, ab[c]); ab[c + 1] = fmaf(pb_[jj], vv.y, ab[c + 1]);
+                    ab[c + 2] = fmaf(pb_[jj], vv.z, ab[c + 2]); ab[c + 3] = fmaf(pb_[jj], vv.w, ab[c + 3]);
+                    if (do_a) {
+                        aa[c] = fmaf(pa_[jj], vv.x, aa[c]); aa[c + 1] = fmaf(pa_[jj], vv.y, aa[c + 1]);
+                        aa[c + 2] = fmaf(pa_[jj], vv.z, aa[c + 2]); aa[c + 3] = fmaf(pa_[jj], vv.w, aa[c + 3]);
+                    }
+                }
+            }
+        }
+        if (act) {
+            const float ib = 1.f / lb;
+            float* ob = o + (t0 + rb) * (size_t)d + h * HD;
+#pragma unroll
+            for (int c = 0; c < HD; c += 4)
+                *reinterpret_cast<float4*>(ob + c) = make_float4(ab[c] * ib, ab[c + 1] * ib, ab[c + 2] * ib, ab[c + 3] * ib);
+            if (two) {
+                const float ia = 1.f / la_;
+                float* oa = o + (t0 + ra) * (size_t)d + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD; c += 4)
+                    *reinterpret_cast<float4*>(oa + c) = make_float4(aa[c] * ia, aa[c + 1] * ia, aa[c + 2] * ia, aa[c + 3] * ia);
+            }
+        }
+    }
+}
+
 // ---- acting: attention of the LAST valid query only (the policy reads q[:, -1, :], agents/dtqn.py:107) ------------------
 // ql [G*n_seq, d] = scaled-later query of the last valid token; kv [T, 2d] = (k | v) of every token.  One warp per
 // (sequence, head): lanes stride over the n_i keys, warp-shuffle softmax, then HD warp reductions for P V.
@@ -211,17 +321,24 @@ template <int HD>
 __global__ void __launch_bounds__(256)
 attn_last_kernel(const float* __restrict__ ql, const float* __restrict__ kv, GroupSrc S, int n_seq, int L, int d,
                  float scale, float* __restrict__ ol) {
+    extern __shared__ float sm_kv[];                           // [L][2d + 4]: (k | v) rows, padded -> conflict-free float4
     const int g = blockIdx.y, i = blockIdx.x;
-    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
     const dtqn_obs_src& s = S.s[g];
     int n = L;
     if (s.timestep) n = min(min(s.ring_len, s.timestep[i] + 1), L);
     const size_t seq = (size_t)g * n_seq + i;
+    const int ld = 2 * d + 4, rq = (2 * d) / 4;
+    const float* kvb = kv + seq * L * (size_t)(2 * d);
+    for (int e = tid; e < n * rq; e += blockDim.x) {
+        const int r = e / rq, c4 = (e % rq) * 4;
+        *reinterpret_cast<float4*>(sm_kv + (size_t)r * ld + c4) = *reinterpret_cast<const float4*>(kvb + (size_t)r * (2 * d) + c4);
+    }
+    __syncthreads();
     const float* qp = ql + seq * d + h * HD;
     float q[HD];
 #pragma unroll
     for (int c = 0; c < HD; ++c) q[c] = qp[c] * scale;
-    const float* kbase = kv + seq * L * (size_t)(2 * d) + h * HD;
     float sc[4];                                               // up to 128 keys: 4 per lane
     float m = -INFINITY;
 #pragma unroll
@@ -229,10 +346,13 @@ attn_last_kernel(const float* __restrict__ ql, const float* __restrict__ kv, Gro
         const int j = lane + 32 * r;
         sc[r] = -INFINITY;
         if (j < n) {
-            const float* kp = kbase + (size_t)j * (2 * d);
+            const float* kp = sm_kv + (size_t)j * ld + h * HD;
             float a = 0.f;
 #pragma unroll
-            for (int c = 0; c < HD; ++c) a = fmaf(q[c], kp[c], a);
+            for (int c = 0; c < HD; c += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kp + c);
+                a = fmaf(q[c], k4.x, a); a = fmaf(q[c + 1], k4.y, a); a = fmaf(q[c + 2], k4.z, a); a = fmaf(q[c + 3], k4.w, a);
+            }
             sc[r] = a;
         }
         m = fmaxf(m, sc[r]);
@@ -247,9 +367,13 @@ attn_last_kernel(const float* __restrict__ ql, const float* __restrict__ kv, Gro
         if (j < n) {
             const float pw = expf(sc[r] - m);
             l += pw;
-            const float* vp = kbase + (size_t)j * (2 * d) + d;
+            const float* vp = sm_kv + (size_t)j * ld + d + h * HD;
 #pragma unroll
-            for (int c = 0; c < HD; ++c) acc[c] = fmaf(pw, vp[c], acc[c]);
+            for (int c = 0; c < HD; c += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(vp + c);
+                acc[c] = fmaf(pw, v4.x, acc[c]); acc[c + 1] = fmaf(pw, v4.y, acc[c + 1]);
+                acc[c + 2] = fmaf(pw, v4.z, acc[c + 2]); acc[c + 3] = fmaf(pw, v4.w, acc[c + 3]);
+            }
         }
     }
     l = warp_sum(l);
@@ -405,15 +529,27 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         if ((rc = linear(a, EPI_BIAS, 4 * li + TC_W_IN))) return rc;
         // attention core
         {
-            dim3 grid(H, (unsigned)(n_seq * G));
-            const int thr = L <= 64 ? 64 : 128;
             const float scale = 1.0f / sqrtf((float)hd);
+            const size_t smem = sizeof(float) * 2 * (size_t)L * d;
+            const bool seq_kernel = H * 32 <= 256 && (hd == 8 || hd == 16);
             prof_begin(PROF_ATTN_FWD, st);
-            if (hd == 8) attn_fwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
-            else if (hd == 16) attn_fwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
-            else if (hd == 32) attn_fwd_kernel<32><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
-            else if (hd == 4) attn_fwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
-            else return DTQN_E_UNSUPPORTED;
+            if (seq_kernel) {
+                if (hd == 8) {
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attn_seq_kernel<8><<<(unsigned)(n_seq * G), 32 * H, smem, st>>>(la.qkv, la.o, L, d, scale);
+                } else {
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_seq_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attn_seq_kernel<16><<<(unsigned)(n_seq * G), 32 * H, smem, st>>>(la.qkv, la.o, L, d, scale);
+                }
+            } else {
+                dim3 grid(H, (unsigned)(n_seq * G));
+                const int thr = L <= 64 ? 64 : 128;
+                if (hd == 8) attn_fwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+                else if (hd == 16) attn_fwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+                else if (hd == 32) attn_fwd_kernel<32><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+                else if (hd == 4) attn_fwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, L, d, scale);
+                else return DTQN_E_UNSUPPORTED;
+            }
             prof_end(PROF_ATTN_FWD, st, 4.0 * (double)T * L * d);      // dense L x L count, as the reference computes it
             DTQN_LAUNCH_CHECK();
         }
@@ -461,10 +597,16 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
             dim3 grid(n_seq, G);
             const float scale = 1.0f / sqrtf((float)hd);
             prof_begin(PROF_ATTN_FWD, st);
-            if (hd == 8) attn_last_kernel<8><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
-            else if (hd == 16) attn_last_kernel<16><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
-            else if (hd == 32) attn_last_kernel<32><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
-            else if (hd == 4) attn_last_kernel<4><<<grid, 32 * H, 0, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            const size_t smem = sizeof(float) * (size_t)L * (2 * d + 4);
+            if (smem > 48 * 1024) {
+                if (hd == 8) cudaFuncSetAttribute(attn_last_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                else if (hd == 16) cudaFuncSetAttribute(attn_last_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                else if (hd == 32) cudaFuncSetAttribute(attn_last_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            }
+            if (hd == 8) attn_last_kernel<8><<<grid, 32 * H, smem, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 16) attn_last_kernel<16><<<grid, 32 * H, smem, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 32) attn_last_kernel<32><<<grid, 32 * H, smem, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
+            else if (hd == 4) attn_last_kernel<4><<<grid, 32 * H, smem, st>>>(qlb, la.qkv, S, n_seq, L, d, scale, olb);
             else return DTQN_E_UNSUPPORTED;
             prof_end(PROF_ATTN_FWD, st, 4.0 * (double)G * n_seq * L * d);
             DTQN_LAUNCH_CHECK();

@@ -184,6 +184,8 @@ int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg);
 int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed, void* stream);
 /* Groups with at least this many tokens use the tcgen05 path (default 4096); smaller ones stay on fp32 CUDA cores. */
 int dtqn_set_tc_min_tokens(int32_t n_tokens);
+/* 1 (default): persistent warp-specialised tcgen05 kernel where the weight image fits in shared memory; 0: simple one. */
+int dtqn_set_tc_pipelined(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 
