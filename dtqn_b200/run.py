@@ -1,0 +1,113 @@
+"""Experiment driver with the reference's command-line flags (run.py:16-184) driving the batched B200 loop.
+
+    python -m dtqn_b200.run --envs DiscreteCarFlag-v0 --in-embed 64 --n-envs 4096
+    torchrun --nproc-per-node 8 -m dtqn_b200.run --envs DiscreteCarFlag-v0 --in-embed 64 --n-envs 4096
+
+One "timestep" of the reference loop (run.py:290) is one lockstep iteration here: every env takes one step and the agent
+takes one gradient step, so ``--num-steps`` iterations collect ``num-steps x n-envs x world`` transitions.  New flag (no
+reference analogue): ``--n-envs`` lockstep environments per GPU.  Logging / wandb / rendering / checkpoint flags are
+accepted for command-line compatibility; losses and evaluation results are printed (rank 0) every ``--eval-frequency``.
+"""
+import argparse
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def get_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--project-name", type=str, default="DTQN-test")
+    p.add_argument("--disable-wandb", action="store_true")
+    p.add_argument("--time-limit", type=float, default=None, help="hours; stop (cleanly) after this long")
+    p.add_argument("--model", type=str, default="DTQN", choices=["DTQN"],
+                   help="only the DTQN family is on the B200 hot path (baselines are out of scope)")
+    p.add_argument("--envs", type=str, nargs="+", default=["DiscreteCarFlag-v0"])
+    p.add_argument("--num-steps", type=int, default=2_000_000)
+    p.add_argument("--tuf", type=int, default=10_000, help="target update frequency (gradient steps)")
+    p.add_argument("--lr", type=float, default=3e-4)
+    p.add_argument("--batch", type=int, default=32)
+    p.add_argument("--buf-size", type=int, default=500_000)
+    p.add_argument("--eval-frequency", type=int, default=5_000)
+    p.add_argument("--eval-episodes", type=int, default=10)
+    p.add_argument("--device", type=str, default="cuda")
+    p.add_argument("--context", type=int, default=50)
+    p.add_argument("--obs-embed", type=int, default=8)
+    p.add_argument("--a-embed", type=int, default=0)
+    p.add_argument("--in-embed", type=int, default=128)
+    p.add_argument("--max-episode-steps", type=int, default=-1)
+    p.add_argument("--seed", type=int, default=1)
+    p.add_argument("--save-policy", action="store_true")
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--render", action="store_true")
+    p.add_argument("--history", type=int, default=50)
+    p.add_argument("--heads", type=int, default=8)
+    p.add_argument("--layers", type=int, default=2)
+    p.add_argument("--dropout", type=float, default=0.0)
+    p.add_argument("--discount", type=float, default=0.99)
+    p.add_argument("--gate", type=str, default="res", choices=["res", "gru"])
+    p.add_argument("--identity", action="store_true")
+    p.add_argument("--pos", default="learned", choices=["learned", "sin", "none"])
+    p.add_argument("--bag-size", type=int, default=0)
+    p.add_argument("--slurm-job-id", default=0, type=str)
+    p.add_argument("--n-envs", type=int, default=4096, help="lockstep environments per GPU (new)")
+    p.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    return p.parse_args(argv)
+
+
+def run_experiment(args):
+    from dtqn_b200.runner import BatchedTrainer
+    if len(args.envs) != 1:
+        raise NotImplementedError("multi-env sampling needs identical spaces (run.py:47); run one trainer per env id")
+    for flag, bad in (("--a-embed", args.a_embed), ("--dropout", args.dropout), ("--identity", args.identity),
+                      ("--bag-size", args.bag_size)):
+        if bad:
+            raise NotImplementedError(f"{flag} is not on the B200 hot path yet (DESIGN.md section 7)")
+    if args.gate != "res":
+        raise NotImplementedError("--gate gru is not on the B200 hot path yet (DESIGN.md section 7)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local) if args.device.startswith("cuda") else torch.device(args.device)
+    tr = BatchedTrainer(args.envs[0], args.n_envs, seed=args.seed, device=device, inner_embed=args.in_embed,
+                        heads=args.heads, layers=args.layers, context=args.context, batch=args.batch,
+                        buf_size=max(args.buf_size, 8 * args.n_envs * 200), lr=args.lr, tuf=args.tuf,
+                        gamma=args.discount, history=args.history, num_steps=args.num_steps, obs_embed=args.obs_embed)
+    rank = tr.rank
+    if rank == 0:
+        n = sum(p.numel() for p in tr.agent.policy_network.parameters())
+        print(f"Creating {args.model} with {n} parameters")                      # run.py:447-450
+    # prepopulate 50 000 transitions (run.py:495) with the random policy, and at least until a batch can be sampled
+    steps = max(1, 50_000 // args.n_envs)
+    tr.prepopulate(steps)
+    while not tr.agent.replay_buffer.can_sample(args.batch):
+        tr.prepopulate(16)
+    if not args.no_graph:
+        tr.enable_graphs()
+    start = time.time()
+    for timestep in range(tr.agent.num_train_steps, args.num_steps):
+        tr.train_iteration()
+        if timestep % args.eval_frequency == 0:
+            sr, ret, length = tr.evaluate(max(1, args.eval_episodes // 10))
+            if rank == 0:
+                a = tr.agent
+                print(f"[{timestep}] env-steps {timestep * args.n_envs * world}  TD {a.td_errors.mean():.5f}  "
+                      f"grad-norm {a.grad_norms.mean():.4f}  Q {a.qvalue_mean.mean():.4f}  "
+                      f"{args.envs[0]}/SuccessRate {sr:.3f}  Return {ret:.3f}  EpisodeLength {length:.1f}  "
+                      f"hours {(time.time() - start) / 3600:.3f}", flush=True)
+        if args.save_policy and timestep % 50_000 == 0 and rank == 0:
+            os.makedirs("policies", exist_ok=True)
+            torch.save(tr.agent.policy_network.state_dict(), os.path.join("policies", f"{args.project_name}_{args.envs[0]}.pt"))
+        if args.time_limit and (time.time() - start) / 3600 >= args.time_limit:
+            break
+    if world > 1:
+        dist.destroy_process_group()
+    return tr
+
+
+if __name__ == "__main__":
+    run_experiment(get_args())
