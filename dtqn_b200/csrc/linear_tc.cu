@@ -318,7 +318,7 @@ int launch_one(const TcArgs& t, int G, cudaStream_t st) {
 //   warps 0-7  (256 thr)  producers: fp32 activations (coalesced) -> bf16 hi/lo -> canonical K-major smem stage
 //   warp  8               one elected thread: TMA bulk load of the weight image (once), tcgen05.mma issue, tcgen05.commit
 //   warps 9-12 (128 thr)  epilogue: tcgen05.ld (thread = row) -> bias / ReLU / residual+LayerNorm -> padded smem staging ->
-//                          one TMA bulk store per row segment (cp.async.bulk.global.shared::cta), double buffered
+//                          full-line coalesced global stores (a thread-per-row store would touch 32 lines per instruction)
 // =================================================================================================================================
 constexpr int PIPE_PRODUCERS = 256;
 constexpr int PIPE_THREADS = PIPE_PRODUCERS + 32 + 128;
@@ -336,6 +336,22 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+
+// Each epilogue warp owns 32 staged rows (padded to STG_ROW_BYTES).  Write them out row-major with full-line stores:
+// lanes 0-15 cover the 256 B of one row, lanes 16-31 the next row.
+__device__ __forceinline__ void warp_store_rows(const uint8_t* stg_warp, float* dst_row0, size_t row_stride_floats,
+                                                int rows_valid, int lane) {
+    __syncwarp();
+    const int half = lane >> 4, c16 = lane & 15;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr += 2) {
+        const int r = rr + half;
+        const float4 v = *reinterpret_cast<const float4*>(stg_warp + r * STG_ROW_BYTES + c16 * 16);
+        if (r < rows_valid) *reinterpret_cast<float4*>(dst_row0 + (size_t)r * row_stride_floats + c16 * 4) = v;
+    }
+    __syncwarp();
+}
 
 template <int N_TILE, int K_CHUNKS, int EPI>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
@@ -398,7 +414,6 @@ linear_tc_pipe_kernel(TcArgs t) {
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
             for (int kc = 0; kc < K_CHUNKS; ++kc, ++it) {
                 const int st = it & 1;
-                if (it >= 2 && !mbar_wait(BAR(A_EMPTY + st), (uint32_t)(((it >> 1) - 1) & 1))) return;
                 uint8_t* dst = sA + st * A_STAGE_BYTES;
                 float4 v[8];
 #pragma unroll
@@ -409,6 +424,8 @@ linear_tc_pipe_kernel(TcArgs t) {
                         v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
                     } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
                 }
+                // the loads above are in flight while we wait for the MMAs that still read this smem stage
+                if (it >= 2 && !mbar_wait(BAR(A_EMPTY + st), (uint32_t)(((it >> 1) - 1) & 1))) return;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int r = q * 32 + (tid >> 3), c = tid & 7;
@@ -465,7 +482,7 @@ linear_tc_pipe_kernel(TcArgs t) {
         const int q4 = warp & 3;                                // TMEM lane quarter this warp may access
         const int row_in_tile = q4 * 32 + lane;
         const int n0 = nt * N_TILE;
-        int round = 0;
+        int round = 0; (void)round;
         for (int i = 0; i < my_tiles; ++i) {
             const int as = i & 1;
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
@@ -474,11 +491,12 @@ linear_tc_pipe_kernel(TcArgs t) {
             const int r = m0 + row_in_tile;
             const bool row_ok = r < a.Tg;
             const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * N_TILE);
+            const int rows_valid = min(32, a.Tg - (m0 + q4 * 32));       // rows of this warp's quarter that exist
             if (EPI != EPI_RES_LN) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
-                    uint8_t* stg = sStg + (round & 1) * STG_BYTES + row_in_tile * STG_ROW_BYTES;
-                    bulk_wait_read<1>();                        // the buffer written two rounds ago has been read out
+                    uint8_t* stg_w = sStg + (round & 1) * STG_BYTES + (q4 * 32) * STG_ROW_BYTES;
+                    uint8_t* stg = stg_w + lane * STG_ROW_BYTES;
 #pragma unroll
                     for (int cc = 0; cc < STG_COLS; cc += 16) {
                         float v[16];
@@ -494,27 +512,49 @@ linear_tc_pipe_kernel(TcArgs t) {
                             *reinterpret_cast<float4*>(stg + (cc + q) * 4) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
-                    fence_async_smem();
-                    if (row_ok) bulk_s2g(a.Y + (grow + r) * (size_t)a.N + n0 + c0, smem_u32(stg), STG_COLS * 4);
-                    bulk_commit();
+                    if (rows_valid > 0)
+                        warp_store_rows(stg_w, a.Y + (grow + m0 + q4 * 32) * (size_t)a.N + n0 + c0, (size_t)a.N, rows_valid, lane);
                 }
             } else {
-                // x_out = LayerNorm(x_res + relu(acc + b)); N_TILE == d_model, the row lives in this thread
+                // x_out = LayerNorm(x_res + relu(acc + b)); N_TILE == d_model, the row lives in this thread.
+                // The residual rows are first pulled into the warp's staging rows with full-line loads.
                 float u[N_TILE];
                 const size_t ro = (grow + (row_ok ? r : 0)) * (size_t)N_TILE;
                 float s = 0.f;
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(trow + c0, v);
+                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS) {
+                    uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
+                    {
+                        __syncwarp();
+                        const int half = lane >> 4, c16 = lane & 15;
+                        const float* src0 = a.R + (grow + m0 + q4 * 32) * (size_t)N_TILE + c0;
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; rr += 2) {
+                            const int rw = rr + half;
+                            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rw < rows_valid) v4 = *reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4);
+                            *reinterpret_cast<float4*>(stg_w + rw * STG_ROW_BYTES + c16 * 16) = v4;
+                        }
+                        __syncwarp();
+                    }
+                    const uint8_t* myrow = stg_w + lane * STG_ROW_BYTES;
 #pragma unroll
-                    for (int q = 0; q < 16; q += 4) {
-                        const float4 xr = *reinterpret_cast<const float4*>(a.R + ro + c0 + q);
-                        const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+                    for (int cc = 0; cc < STG_COLS; cc += 16) {
+                        float v[16];
+                        tmem_ld16(trow + c0 + cc, v);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            u[c0 + q + e] = xv[e] + fmaxf(v[q + e] + sBias[c0 + q + e], 0.f);
-                            s += u[c0 + q + e];
+                        for (int q = 0; q < 16; q += 4) {
+                            const float4 xr = *reinterpret_cast<const float4*>(myrow + (cc + q) * 4);
+                            const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+                            float rl[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                rl[e] = fmaxf(v[q + e] + sBias[c0 + cc + q + e], 0.f);
+                                u[c0 + cc + q + e] = xv[e] + rl[e];
+                                s += u[c0 + cc + q + e];
+                            }
+                            if (a.r_save && row_ok)
+                                *reinterpret_cast<float4*>(a.r_save + ro + c0 + cc + q) = make_float4(rl[0], rl[1], rl[2], rl[3]);
                         }
                     }
                 }
@@ -523,10 +563,11 @@ linear_tc_pipe_kernel(TcArgs t) {
 #pragma unroll
                 for (int j = 0; j < N_TILE; ++j) { const float dl = u[j] - mean; vs = fmaf(dl, dl, vs); }
                 const float rstd = 1.0f / sqrtf(vs * (1.f / N_TILE) + 1e-5f);
+                if (a.st_save && row_ok) { a.st_save[(grow + r) * 2] = mean; a.st_save[(grow + r) * 2 + 1] = rstd; }
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
-                    uint8_t* stg = sStg + (round & 1) * STG_BYTES + row_in_tile * STG_ROW_BYTES;
-                    bulk_wait_read<1>();
+                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS) {
+                    uint8_t* stg_w = sStg + STG_BYTES + (q4 * 32) * STG_ROW_BYTES;
+                    uint8_t* stg = stg_w + lane * STG_ROW_BYTES;
 #pragma unroll
                     for (int q = 0; q < STG_COLS; q += 4) {
                         float o[4];
@@ -535,15 +576,13 @@ linear_tc_pipe_kernel(TcArgs t) {
                             o[e] = (u[c0 + q + e] - mean) * rstd * sBias[N_TILE + c0 + q + e] + sBias[2 * N_TILE + c0 + q + e];
                         *reinterpret_cast<float4*>(stg + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    fence_async_smem();
-                    if (row_ok) bulk_s2g(a.Y + ro + c0, smem_u32(stg), STG_COLS * 4);
-                    bulk_commit();
+                    if (rows_valid > 0)
+                        warp_store_rows(stg_w, a.Y + (grow + m0 + q4 * 32) * (size_t)N_TILE + c0, (size_t)N_TILE, rows_valid, lane);
                 }
             }
             tc_fence_before();
             mbar_arrive(BAR(ACC_EMPTY + as));                   // accumulator stage drained
         }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all row stores complete before smem goes away
     }
     tc_fence_before();
     __syncthreads();

@@ -385,6 +385,35 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
     }
 }
 
+
+// The weight-gradient GEMMs only feed the flat gradient buffer, so they run on a side stream, forked after the kernel
+// that produces their dY operand and joined at the end of every layer (before the dY buffers are overwritten).  Under
+// CUDA-graph capture the event record / wait pairs become graph edges.  The stream and events are created once per process.
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8];
+    int next = 0;
+    bool ok = false;
+    void init() {
+        if (ok) return;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return;
+        for (int i = 0; i < 8; ++i) if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+        ok = true;
+    }
+    void fork(cudaStream_t main_st) {           // side stream waits for everything issued on main so far
+        cudaEvent_t e = ev[next]; next = (next + 1) & 7;
+        cudaEventRecord(e, main_st);
+        cudaStreamWaitEvent(st, e, 0);
+    }
+    void join(cudaStream_t main_st) {           // main waits for everything issued on the side stream so far
+        cudaEvent_t e = ev[next]; next = (next + 1) & 7;
+        cudaEventRecord(e, st);
+        cudaStreamWaitEvent(main_st, e, 0);
+    }
+};
+SideStream g_side;
+int g_parallel_wgrad = 1;
+
 template <int EPI>
 int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
     dim3 grid(dtqn_cdiv(T, GEMM_BM), 1, 1);
@@ -408,7 +437,7 @@ int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* 
 }
 
 struct BwdScratch {
-    float *dq, *g_hh, *gx, *gu, *ga, *gh, *gqkv, *go, *gx1, *partial;
+    float *dq, *g_hh, *gx, *gu, *ga, *ga1, *gh, *gqkv, *go, *gx1, *partial;
     unsigned* ticket;
     long long total;
 };
@@ -417,7 +446,7 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
     long long o = 0;
     auto take = [&](long long n) { float* p = base ? base + o : nullptr; o = al4(o + n); return p; };
     s.dq = take(T0 * c.num_actions); s.g_hh = take(T0 * d); s.gx = take(T0 * d); s.gu = take(T0 * d);
-    s.ga = take(T0 * d); s.gh = take(T0 * 4 * d); s.gqkv = take(T0 * 3 * d); s.go = take(T0 * d); s.gx1 = take(T0 * d);
+    s.ga = take(T0 * d); s.ga1 = take(T0 * d); s.gh = take(T0 * 4 * d); s.gqkv = take(T0 * 3 * d); s.go = take(T0 * d); s.gx1 = take(T0 * d);
     s.partial = take((long long)dtqn_cdiv(T0, 256) * 8);
     s.ticket = reinterpret_cast<unsigned*>(take(4));
     s.total = o;
@@ -425,6 +454,8 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
 }
 
 }  // namespace
+
+extern "C" int dtqn_set_parallel_wgrad(int32_t on) { g_parallel_wgrad = on; return 0; }
 
 extern "C" int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len) {
     if (!cfg || batch < 1 || seq_len < 1) return DTQN_E_ARG;
@@ -462,8 +493,13 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
                                                         grads + lay.h2_w, grads + lay.h2_b);
     prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();
+    g_side.init();
+    const bool par = g_parallel_wgrad && g_side.ok;
+    cudaStream_t ws_ = par ? g_side.st : st;                       // stream of the weight-gradient GEMMs
+    auto fork = [&]() { if (par) g_side.fork(st); };
     const float* x_last = act.layer[cfg->n_layers - 1].x2;
-    if ((rc = launch_wgrad(s.g_hh, x_last, Ti, d, d, grads + lay.h1_w, grads + lay.h1_b, st))) return rc;
+    fork();
+    if ((rc = launch_wgrad(s.g_hh, x_last, Ti, d, d, grads + lay.h1_w, grads + lay.h1_b, ws_))) return rc;
     if ((rc = launch_dgrad<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, s.gx, Ti, d, d, st))) return rc;
     for (int li = cfg->n_layers - 1; li >= 0; --li) {
         const LayerOff& lo = lay.layer[li];
@@ -476,20 +512,23 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // ffn.2
-        if ((rc = launch_wgrad(s.ga, la.h, Ti, d, 4 * d, grads + lo.f2_w, grads + lo.f2_b, st))) return rc;
+        fork();
+        if ((rc = launch_wgrad(s.ga, la.h, Ti, d, 4 * d, grads + lo.f2_w, grads + lo.f2_b, ws_))) return rc;
         if ((rc = launch_dgrad<DG_MASK>(s.ga, params + lo.f2_w, la.h, s.gh, Ti, d, 4 * d, st))) return rc;
         // ffn.0
-        if ((rc = launch_wgrad(s.gh, la.x1, Ti, 4 * d, d, grads + lo.f1_w, grads + lo.f1_b, st))) return rc;
+        fork();
+        if ((rc = launch_wgrad(s.gh, la.x1, Ti, 4 * d, d, grads + lo.f1_w, grads + lo.f1_b, ws_))) return rc;
         if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
-        // LN1 backward: dy = gx1 -> gu (du1), ga (d out_proj output)
+        // LN1 backward: dy = gx1 -> gu (du1), ga1 (d out_proj output)
         prof_begin(PROF_LN_BWD, st);
-        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
-        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga, grads + lo.ln1_w, grads + lo.ln1_b);
+        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b);
+        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b);
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // out_proj
-        if ((rc = launch_wgrad(s.ga, la.o, Ti, d, d, grads + lo.out_w, grads + lo.out_b, st))) return rc;
-        if ((rc = launch_dgrad<DG_NONE>(s.ga, params + lo.out_w, nullptr, s.go, Ti, d, d, st))) return rc;
+        fork();
+        if ((rc = launch_wgrad(s.ga1, la.o, Ti, d, d, grads + lo.out_w, grads + lo.out_b, ws_))) return rc;
+        if ((rc = launch_dgrad<DG_NONE>(s.ga1, params + lo.out_w, nullptr, s.go, Ti, d, d, st))) return rc;
         // attention core
         {
             dim3 grid(H, (unsigned)B);
@@ -504,8 +543,10 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
             DTQN_LAUNCH_CHECK();
         }
         // in_proj
-        if ((rc = launch_wgrad(s.gqkv, x_in, Ti, 3 * d, d, grads + lo.in_w, grads + lo.in_b, st))) return rc;
+        fork();
+        if ((rc = launch_wgrad(s.gqkv, x_in, Ti, 3 * d, d, grads + lo.in_w, grads + lo.in_b, ws_))) return rc;
         if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
+        if (par) g_side.join(st);          // the next layer overwrites ga / gh / gqkv / ga1
     }
     // embedding + position table
     prof_begin(PROF_OTHER, st);

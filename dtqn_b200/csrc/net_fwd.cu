@@ -226,6 +226,7 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
     __syncthreads();
     const int h = tid >> 5, lane = tid & 31;
     const int half = (L + 1) / 2;
+    scale *= 1.4426950408889634f;                             // softmax in base 2: exp(x) = exp2(x * log2 e), one MUFU per term
     for (int r0 = 0; r0 < half; r0 += 32) {                  // L <= 64: one pass; L = 128: two
         const int r = r0 + lane;
         const bool act = r < half;
@@ -264,18 +265,18 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
                 sb[jj] = (j0 + jj <= rb) ? db : -INFINITY;
             }
             const float nmb = fmaxf(mb, fmaxf(fmaxf(sb[0], sb[1]), fmaxf(sb[2], sb[3])));
-            const float cb = expf(mb - nmb);
+            const float cb = exp2f(mb - nmb);
             float pb_[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) pb_[jj] = expf(sb[jj] - nmb);
+            for (int jj = 0; jj < 4; ++jj) pb_[jj] = exp2f(sb[jj] - nmb);
             lb = lb * cb + (pb_[0] + pb_[1]) + (pb_[2] + pb_[3]);
             mb = nmb;
             float ca = 1.f, pa_[4] = {0.f, 0.f, 0.f, 0.f};
             if (do_a) {
                 const float nma = fmaxf(ma, fmaxf(fmaxf(sa[0], sa[1]), fmaxf(sa[2], sa[3])));
-                ca = expf(ma - nma);
+                ca = exp2f(ma - nma);
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) pa_[jj] = expf(sa[jj] - nma);
+                for (int jj = 0; jj < 4; ++jj) pa_[jj] = exp2f(sa[jj] - nma);
                 la_ = la_ * ca + (pa_[0] + pa_[1]) + (pa_[2] + pa_[3]);
                 ma = nma;
             }
@@ -473,7 +474,7 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
 }
 
 // tokens per group from which the tcgen05 path (bf16x3 split, 128-row tiles) replaces the fp32 CUDA-core GEMMs
-static int g_tc_min_tokens = 4096;
+static int g_tc_min_tokens = 1024;
 extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }
 
 extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const void* const* packed,

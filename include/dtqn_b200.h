@@ -182,7 +182,7 @@ int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* 
  * [N_TILE x 64] block with one TMA bulk copy.  Re-pack after every optimiser step / target update. */
 int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg);
 int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed, void* stream);
-/* Groups with at least this many tokens use the tcgen05 path (default 4096); smaller ones stay on fp32 CUDA cores. */
+/* Groups with at least this many tokens use the tcgen05 path (default 1024); smaller ones stay on fp32 CUDA cores. */
 int dtqn_set_tc_min_tokens(int32_t n_tokens);
 /* 1 (default): persistent warp-specialised tcgen05 kernel where the weight image fits in shared memory; 0: simple one. */
 int dtqn_set_tc_pipelined(int32_t on);
@@ -200,6 +200,9 @@ int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* policy_params, const 
                      int64_t workspace_floats, float* scratch /* >= dtqn_td_scratch_floats */, float* grads,
                      float* stats_out, void* stream);
 int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len);
+/* 1 (default): weight-gradient GEMMs run on a library-owned side stream, forked / joined with events around each layer
+ * (graph edges under capture); 0: everything on the caller's stream. */
+int dtqn_set_parallel_wgrad(int32_t on);
 
 /* clip_grad_norm_(params, max_norm, error_if_nonfinite=True) + Adam.step (dtqn/agents/dtqn.py:257-265,
  * dtqn/agents/dqn.py:64): grads *= grad_scale (1/world after the allreduce), total = ||grads||_2,

@@ -155,7 +155,7 @@ def test_tcgen05_forward_vs_oracle(golden_dir, env):
         ref = onet.forward(sd, x, 8).numpy()
     networks.set_tc_min_tokens(1 << 30)
     q_simt = net(x).cpu().numpy()
-    networks.set_tc_min_tokens(4096)
+    networks.set_tc_min_tokens(1024)
     errs = {}
     for pipelined in (1, 0):            # persistent warp-specialised kernel, then the simple one-tile-per-CTA kernel
         _lib.lib.dtqn_set_tc_pipelined(pipelined)
