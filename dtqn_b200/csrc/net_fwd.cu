@@ -473,8 +473,10 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
     return net_act_layout(*cfg, n_tokens, save, nullptr, A);
 }
 
-// tokens per group from which the tcgen05 path (bf16x3 split, 128-row tiles) replaces the fp32 CUDA-core GEMMs
-static int g_tc_min_tokens = 1024;
+// tokens per group from which the tcgen05 path (bf16x3 split, 128-row tiles) replaces the fp32 CUDA-core GEMMs.
+// The 32 x 50-token training groups stay on fp32 CUDA cores: they are latency-bound either way (measured: no faster on
+// tensor cores) and the exact-fp32 forward keeps ReLU masks -- hence gradients -- closest to the reference's.
+static int g_tc_min_tokens = 4096;
 extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }
 
 extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const void* const* packed,

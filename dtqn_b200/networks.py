@@ -236,7 +236,7 @@ def forward_groups(net: DTQN, nets, srcs, n_seq: int, L: int, q_mode: int, save:
 
 
 def set_tc_min_tokens(n: int) -> None:
-    """Groups with >= n tokens run their GEMMs on the tcgen05 path (default 1024)."""
+    """Groups with >= n tokens run their GEMMs on the tcgen05 path (default 4096)."""
     _l.dtqn_set_tc_min_tokens(int(n))
 
 

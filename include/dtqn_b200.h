@@ -182,7 +182,7 @@ int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* 
  * [N_TILE x 64] block with one TMA bulk copy.  Re-pack after every optimiser step / target update. */
 int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg);
 int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed, void* stream);
-/* Groups with at least this many tokens use the tcgen05 path (default 1024); smaller ones stay on fp32 CUDA cores. */
+/* Groups with at least this many tokens use the tcgen05 path (default 4096); smaller ones stay on fp32 CUDA cores. */
 int dtqn_set_tc_min_tokens(int32_t n_tokens);
 /* 1 (default): persistent warp-specialised tcgen05 kernel where the weight image fits in shared memory; 0: simple one. */
 int dtqn_set_tc_pipelined(int32_t on);
