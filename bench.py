@@ -258,15 +258,16 @@ def main():
     # ---- roofline of the dominant kernel: CUDA events around every launch of the tagged kernel, in a dedicated pass ----
     roof = None
     launches = None
+    lib = _lib.lib
+    lib.dtqn_profile_enable.argtypes = [C.c_int32]
+    lib.dtqn_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    psteps = min(10, args.steps)
     if rank == 0:
-        lib = _lib.lib
-        lib.dtqn_profile_enable.argtypes = [C.c_int32]
-        lib.dtqn_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         lib.dtqn_profile_enable(1)
-        psteps = min(10, args.steps)
-        for _ in range(psteps):
-            tr.train_iteration()
-        torch.cuda.synchronize()
+    for _ in range(psteps):                 # every rank runs the pass (the loop contains the gradient collective)
+        tr.train_iteration()
+    barrier()
+    if rank == 0:
         tags = {}
         names = ["linear_fwd", "attn_fwd", "env_step", "env_roll", "replay_gather", "dgrad", "wgrad", "attn_bwd", "ln_bwd",
                  "embed", "head", "td_loss", "clip_adam", "other"]
