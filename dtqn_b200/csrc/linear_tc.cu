@@ -408,36 +408,47 @@ linear_tc_pipe_kernel(TcArgs t) {
 
     if (warp < 8) {
         // ------------------------------------------------ producers ------------------------------------------------
+        // Two register sets: the global loads of item i+1 are issued before item i is converted, so ~2 tiles (64 KB) of
+        // reads are in flight per SM while the MMA / epilogue of earlier tiles run.
         const float* X = a.X + grow * a.K;
-        int it = 0;
-        for (int i = 0; i < my_tiles; ++i) {
+        const int items = my_tiles * K_CHUNKS;
+        auto issue = [&](int it, float4 (&v)[8]) {
+            const int i = it / K_CHUNKS, kc = it % K_CHUNKS;
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
-            for (int kc = 0; kc < K_CHUNKS; ++kc, ++it) {
-                const int st = it & 1;
-                uint8_t* dst = sA + st * A_STAGE_BYTES;
-                float4 v[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {                  // 32 rows x 64 floats per pass; a warp reads 4 rows x 256 B
-                    const int r = q * 32 + (tid >> 3), c = tid & 7;
-                    if (m0 + r < a.Tg) {
-                        const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + kc * TC_KC + c * 8);
-                        v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
-                    } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
-                }
-                // the loads above are in flight while we wait for the MMAs that still read this smem stage
-                if (it >= 2 && !mbar_wait(BAR(A_EMPTY + st), (uint32_t)(((it >> 1) - 1) & 1))) return;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = q * 32 + (tid >> 3), c = tid & 7;
-                    const float x[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-                    uint4 hi, lo;
-                    split8(x, hi, lo);
-                    *reinterpret_cast<uint4*>(dst + c * A_CHUNK_STRIDE + r * 16) = hi;
-                    *reinterpret_cast<uint4*>(dst + A_HALF_BYTES + c * A_CHUNK_STRIDE + r * 16) = lo;
-                }
-                fence_async_smem();
-                mbar_arrive(BAR(A_FULL + st));
+            for (int q = 0; q < 4; ++q) {                      // 32 rows x 64 floats per pass; a warp reads 4 rows x 256 B
+                const int r = q * 32 + (tid >> 3), c = tid & 7;
+                if (m0 + r < a.Tg) {
+                    const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + kc * TC_KC + c * 8);
+                    v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
+                } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
             }
+        };
+        auto finish = [&](int it, float4 (&v)[8]) -> bool {
+            const int st = it & 1;
+            if (it >= 2 && !mbar_wait(BAR(A_EMPTY + st), (uint32_t)(((it >> 1) - 1) & 1))) return false;
+            uint8_t* dst = sA + st * A_STAGE_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + (tid >> 3), c = tid & 7;
+                const float x[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(dst + c * A_CHUNK_STRIDE + r * 16) = hi;
+                *reinterpret_cast<uint4*>(dst + A_HALF_BYTES + c * A_CHUNK_STRIDE + r * 16) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(BAR(A_FULL + st));
+            return true;
+        };
+        float4 va[8], vb[8];
+        if (items > 0) issue(0, va);
+        bool okp = true;
+        for (int it = 0; it < items && okp; it += 2) {
+            if (it + 1 < items) issue(it + 1, vb);
+            okp = finish(it, va);
+            if (it + 2 < items) issue(it + 2, va);
+            if (okp && it + 1 < items) okp = finish(it + 1, vb);
         }
     } else if (warp == 8) {
         // ------------------------------------------------ MMA issuer ------------------------------------------------
@@ -486,12 +497,26 @@ linear_tc_pipe_kernel(TcArgs t) {
         for (int i = 0; i < my_tiles; ++i) {
             const int as = i & 1;
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
+            const int rows_valid = min(32, a.Tg - (m0 + q4 * 32));       // rows of this warp's quarter that exist
+            if (EPI == EPI_RES_LN && N_TILE <= STG_COLS) {
+                // pull this warp's residual rows into its staging rows with full-line loads while the MMAs still run
+                uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
+                const int half = lane >> 4, c16 = lane & 15;
+                const float* src0 = a.R + (grow + m0 + q4 * 32) * (size_t)N_TILE;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int rw = rr + half;
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rw < rows_valid) v4 = *reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4);
+                    *reinterpret_cast<float4*>(stg_w + rw * STG_ROW_BYTES + c16 * 16) = v4;
+                }
+                __syncwarp();
+            }
             if (!mbar_wait(BAR(ACC_FULL + as), (uint32_t)((i >> 1) & 1))) break;
             tc_fence_after();
             const int r = m0 + row_in_tile;
             const bool row_ok = r < a.Tg;
             const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * N_TILE);
-            const int rows_valid = min(32, a.Tg - (m0 + q4 * 32));       // rows of this warp's quarter that exist
             if (EPI != EPI_RES_LN) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
@@ -524,7 +549,7 @@ linear_tc_pipe_kernel(TcArgs t) {
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS) {
                     uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
-                    {
+                    if (N_TILE > STG_COLS) {
                         __syncwarp();
                         const int half = lane >> 4, c16 = lane & 15;
                         const float* src0 = a.R + (grow + m0 + q4 * 32) * (size_t)N_TILE + c0;

@@ -66,6 +66,61 @@ embed_kernel(GroupPtrs P, GroupSrc S, dtqn_net_cfg c, long long emb_table, long 
     *reinterpret_cast<float4*>(x0 + ((long long)g * Tg + t) * d + c0) = out;
 }
 
+
+// Continuous observations, fast path: 64 tokens per CTA.  Observation rows (ring-resolved) and the tiny Linear(O, d)
+// are staged in shared memory once; each thread then emits 16 contiguous channels of one token (4 threads = one 256 B row).
+template <int D>
+__global__ void __launch_bounds__(256)
+embed_cont_kernel(GroupPtrs P, GroupSrc S, int O, long long emb_w, long long emb_b, long long pos_off, int n_seq, int L,
+                  float obs_mask, float* __restrict__ x0) {
+    constexpr int TOK = 1024 / (D / 16) / 4;                  // tokens per CTA: 64 (D = 64) or 32 (D = 128)
+    __shared__ float sW[D * 16];
+    __shared__ float sB[D];
+    __shared__ float sObs[TOK][16];
+    const int g = blockIdx.z, tid = threadIdx.x;
+    const float* p = P.p[g];
+    const long long Tg = (long long)n_seq * L;
+    const long long t0 = (long long)blockIdx.x * TOK;
+    for (int e = tid; e < D * O; e += 256) sW[e] = __ldg(p + emb_w + e);
+    for (int e = tid; e < D; e += 256) sB[e] = __ldg(p + emb_b + e);
+    if (tid < TOK) {
+        const long long t = t0 + tid;
+        if (t < Tg) {
+            const int i = (int)(t / L), j = (int)(t % L);
+            const dtqn_obs_src& s = S.s[g];
+            int row = j; bool valid = true;
+            if (s.timestep) {
+                const int ts = s.timestep[i];
+                const int n = min(s.ring_len, ts + 1);
+                valid = j < n;
+                row = valid ? (ts + 1 - n + j) % s.ring_len : 0;
+            }
+            const float* o = s.obs + (long long)i * s.seq_stride + (long long)row * O;
+            for (int k = 0; k < O; ++k) sObs[tid][k] = valid ? __ldg(o + k) : obs_mask;
+        }
+    }
+    __syncthreads();
+    constexpr int TPT = D / 16;                               // threads per token
+    const int tl = tid / TPT, c0 = (tid % TPT) * 16;
+    const long long t = t0 + tl;
+    if (tl >= TOK || t >= Tg) return;
+    const int j = (int)(t % L);
+    float ov[16];
+    for (int k = 0; k < O; ++k) ov[k] = sObs[tl][k];
+    const float* pp = p + pos_off + (long long)j * D + c0;
+    float* out = x0 + ((long long)g * Tg + t) * D + c0;
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+        const float4 pv = *reinterpret_cast<const float4*>(pp + q);
+        float acc[4] = {sB[c0 + q], sB[c0 + q + 1], sB[c0 + q + 2], sB[c0 + q + 3]};
+        for (int k = 0; k < O; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(ov[k], sW[(c0 + q + e) * O + k], acc[e]);
+        }
+        *reinterpret_cast<float4*>(out + q) = make_float4(acc[0] + pv.x, acc[1] + pv.y, acc[2] + pv.z, acc[3] + pv.w);
+    }
+}
+
 // ---- Linear with fused epilogues --------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
@@ -510,10 +565,15 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         return launch_linear<EPI_RES_LN>(a, G, d, st);
     };
     {
-        dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
         prof_begin(PROF_EMBED, st);
-        embed_kernel<<<grid, 256, 0, st>>>(P, S, *cfg, lay.emb_table, lay.emb_w, lay.emb_b, lay.pos, n_seq, L,
-                                            cfg->discrete ? (float)(cfg->vocab - 1) : -5.0f, act.x0);
+        if (!cfg->discrete && cfg->obs_dim <= 16) {
+            if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
+            else         embed_cont_kernel<128><<<dim3(dtqn_cdiv(Tg, 32), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
+        } else {
+            dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
+            embed_kernel<<<grid, 256, 0, st>>>(P, S, *cfg, lay.emb_table, lay.emb_w, lay.emb_b, lay.pos, n_seq, L,
+                                                cfg->discrete ? (float)(cfg->vocab - 1) : -5.0f, act.x0);
+        }
         prof_end(PROF_EMBED, st, 2.0 * (double)T * lay.k_in * d);
         DTQN_LAUNCH_CHECK();
     }
