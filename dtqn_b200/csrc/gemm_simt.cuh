@@ -1,5 +1,5 @@
 // fp32 CUDA-core GEMM tile used for the small / latency-bound contractions of the DTQN hot path (train batch of
-// 32 x 50 tokens, K = 64..512) and for every backward GEMM.  64 x BN output tile per 256-thread CTA, BK = 16,
+// 32 x 50 tokens, K = 64..512) and for every backward GEMM.  64 x BN output tile per 256-thread CTA, BK = 32,
 // register prefetch of the next k-slab, conflict-free float4 shared-memory reads.
 //   NT:  C[M,N] = A[M,K] * W[N,K]^T   (forward Linear: x W^T)            B_NN = false
 //   NN:  C[M,N] = A[M,K] * B[K,N]     (dgrad: dY W)                      B_NN = true
@@ -7,7 +7,7 @@
 #include "common.cuh"
 
 #define GEMM_BM 64
-#define GEMM_BK 16
+#define GEMM_BK 32
 #define GEMM_THREADS 256
 
 template <int BN>
@@ -25,7 +25,9 @@ __device__ __forceinline__ void gemm_tile_64(const float* __restrict__ A, int ld
                                              const float* __restrict__ B, int ldb, int K, int m0, int n0,
                                              float (&acc)[4][BN / 16], GemmSmem<BN>& sm) {
     constexpr int TN = BN / 16;
-    constexpr int BV = BN / 64;                 // float4 loads of the B slab per thread
+    constexpr int AV = GEMM_BM * GEMM_BK / 4 / GEMM_THREADS;   // float4 loads of the A slab per thread (2)
+    constexpr int BV = BN * GEMM_BK / 4 / GEMM_THREADS;        // float4 loads of the B slab per thread (2 or 4)
+    constexpr int KQ = GEMM_BK / 4;                            // float4 per slab row along k
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll
@@ -33,28 +35,35 @@ __device__ __forceinline__ void gemm_tile_64(const float* __restrict__ A, int ld
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    // A slab: 64 rows x 16 k  -> one float4 (along k) per thread
-    const int a_row = tid >> 2, a_kq = tid & 3;
-    const bool a_ok = (m0 + a_row) < M;
-    const float* a_ptr = A + (size_t)(m0 + a_row) * lda + a_kq * 4;
-    float4 a_reg, b_reg[BV];
+    float4 a_reg[AV], b_reg[BV];
     auto load_slab = [&](int k0) {
-        a_reg = a_ok ? *reinterpret_cast<const float4*>(a_ptr + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < AV; ++v) {   // A slab: 64 rows x BK k, float4 along k
+            const int idx = tid + v * GEMM_THREADS;
+            const int row = idx / KQ, kq = idx % KQ;
+            a_reg[v] = (m0 + row) < M ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + k0 + kq * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int v = 0; v < BV; ++v) {
             const int idx = tid + v * GEMM_THREADS;
-            if (B_NN) {   // B[k0 + kr, n0 + nq*4 ..]  (16 x BN slab, N contiguous)
+            if (B_NN) {   // B[k0 + kr, n0 + nq*4 ..]  (BK x BN slab, N contiguous)
                 const int kr = idx / (BN / 4), nq = idx % (BN / 4);
                 b_reg[v] = *reinterpret_cast<const float4*>(B + (size_t)(k0 + kr) * ldb + n0 + nq * 4);
-            } else {      // W[n0 + nr, k0 + kq*4 ..]  (BN x 16 slab, K contiguous)
-                const int nr = idx >> 2, kq = idx & 3;
+            } else {      // W[n0 + nr, k0 + kq*4 ..]  (BN x BK slab, K contiguous)
+                const int nr = idx / KQ, kq = idx % KQ;
                 b_reg[v] = *reinterpret_cast<const float4*>(B + (size_t)(n0 + nr) * ldb + k0 + kq * 4);
             }
         }
     };
     auto store_slab = [&]() {
-        sm.As[a_kq * 4 + 0][a_row] = a_reg.x; sm.As[a_kq * 4 + 1][a_row] = a_reg.y;
-        sm.As[a_kq * 4 + 2][a_row] = a_reg.z; sm.As[a_kq * 4 + 3][a_row] = a_reg.w;
+#pragma unroll
+        for (int v = 0; v < AV; ++v) {
+            const int idx = tid + v * GEMM_THREADS;
+            const int row = idx / KQ, kq = idx % KQ;
+            sm.As[kq * 4 + 0][row] = a_reg[v].x; sm.As[kq * 4 + 1][row] = a_reg[v].y;
+            sm.As[kq * 4 + 2][row] = a_reg[v].z; sm.As[kq * 4 + 3][row] = a_reg[v].w;
+        }
 #pragma unroll
         for (int v = 0; v < BV; ++v) {
             const int idx = tid + v * GEMM_THREADS;
@@ -62,7 +71,7 @@ __device__ __forceinline__ void gemm_tile_64(const float* __restrict__ A, int ld
                 const int kr = idx / (BN / 4), nq = idx % (BN / 4);
                 *reinterpret_cast<float4*>(&sm.Bs[kr][nq * 4]) = b_reg[v];
             } else {
-                const int nr = idx >> 2, kq = idx & 3;
+                const int nr = idx / KQ, kq = idx % KQ;
                 sm.Bs[kq * 4 + 0][nr] = b_reg[v].x; sm.Bs[kq * 4 + 1][nr] = b_reg[v].y;
                 sm.Bs[kq * 4 + 2][nr] = b_reg[v].z; sm.Bs[kq * 4 + 3][nr] = b_reg[v].w;
             }

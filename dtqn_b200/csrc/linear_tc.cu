@@ -344,7 +344,7 @@ __device__ __forceinline__ void warp_store_rows(const uint8_t* stg_warp, float* 
                                                 int rows_valid, int lane) {
     __syncwarp();
     const int half = lane >> 4, c16 = lane & 15;
-#pragma unroll 4
+#pragma unroll 8
     for (int rr = 0; rr < 32; rr += 2) {
         const int r = rr + half;
         const float4 v = *reinterpret_cast<const float4*>(stg_warp + r * STG_ROW_BYTES + c16 * 16);
@@ -503,13 +503,16 @@ linear_tc_pipe_kernel(TcArgs t) {
                 uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
                 const int half = lane >> 4, c16 = lane & 15;
                 const float* src0 = a.R + (grow + m0 + q4 * 32) * (size_t)N_TILE;
-#pragma unroll 4
-                for (int rr = 0; rr < 32; rr += 2) {
-                    const int rw = rr + half;
-                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rw < rows_valid) v4 = *reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4);
-                    *reinterpret_cast<float4*>(stg_w + rw * STG_ROW_BYTES + c16 * 16) = v4;
+                float4 rv[16];                                 // all 16 loads in flight before the first smem store
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int rw = 2 * rr + half;
+                    rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rw < rows_valid) rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4));
                 }
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr)
+                    *reinterpret_cast<float4*>(stg_w + (2 * rr + half) * STG_ROW_BYTES + c16 * 16) = rv[rr];
                 __syncwarp();
             }
             if (!mbar_wait(BAR(ACC_FULL + as), (uint32_t)((i >> 1) & 1))) break;
@@ -553,13 +556,16 @@ linear_tc_pipe_kernel(TcArgs t) {
                         __syncwarp();
                         const int half = lane >> 4, c16 = lane & 15;
                         const float* src0 = a.R + (grow + m0 + q4 * 32) * (size_t)N_TILE + c0;
-#pragma unroll 4
-                        for (int rr = 0; rr < 32; rr += 2) {
-                            const int rw = rr + half;
-                            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rw < rows_valid) v4 = *reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4);
-                            *reinterpret_cast<float4*>(stg_w + rw * STG_ROW_BYTES + c16 * 16) = v4;
+                        float4 rv[16];
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const int rw = 2 * rr + half;
+                            rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rw < rows_valid) rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4));
                         }
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr)
+                            *reinterpret_cast<float4*>(stg_w + (2 * rr + half) * STG_ROW_BYTES + c16 * 16) = rv[rr];
                         __syncwarp();
                     }
                     const uint8_t* myrow = stg_w + lane * STG_ROW_BYTES;
