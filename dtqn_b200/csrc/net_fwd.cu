@@ -265,20 +265,32 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
 // Lane r owns the query rows a = r and b = L-1-r, whose causal key ranges [0,a] and [0,b] add up to L+1 keys for every
 // lane: the two rows are processed back to back in blocks of 4 keys (one online-softmax rescale per block, base-2
 // exponentials), so all active lanes run the same number of blocks and no lane idles above its diagonal.
+__device__ __forceinline__ float ex2_approx(float x) {        // MUFU.EX2: x <= 0 here, so no overflow / denormal handling needed
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(256)
 attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int d, float scale) {
     extern __shared__ float sm_kv[];
     const int ld = d + 4;
+    const int Lp = L + 4;                                     // 4 zero rows of padding: a key block may run past the last key
     float* Ks = sm_kv;
-    float* Vs = sm_kv + (size_t)L * ld;
+    float* Vs = sm_kv + (size_t)Lp * ld;
     const size_t t0 = (size_t)blockIdx.x * L;
     const int tid = threadIdx.x, dq = d / 4;
-    for (int e = tid; e < L * dq; e += blockDim.x) {
+    for (int e = tid; e < Lp * dq; e += blockDim.x) {
         const int r = e / dq, c4 = (e % dq) * 4;
-        const float* base = qkv + (t0 + r) * (size_t)(3 * d) + c4;
-        *reinterpret_cast<float4*>(Ks + (size_t)r * ld + c4) = *reinterpret_cast<const float4*>(base + d);
-        *reinterpret_cast<float4*>(Vs + (size_t)r * ld + c4) = *reinterpret_cast<const float4*>(base + 2 * d);
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (r < L) {
+            const float* base = qkv + (t0 + r) * (size_t)(3 * d) + c4;
+            kv = *reinterpret_cast<const float4*>(base + d);
+            vv = *reinterpret_cast<const float4*>(base + 2 * d);
+        }
+        *reinterpret_cast<float4*>(Ks + (size_t)r * ld + c4) = kv;
+        *reinterpret_cast<float4*>(Vs + (size_t)r * ld + c4) = vv;
     }
     __syncthreads();
     const int h = tid >> 5, lane = tid & 31;
@@ -293,6 +305,7 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
         const int nb = act ? (rb + 4) / 4 : 0;
         const int nblk = __reduce_max_sync(0xffffffffu, na + nb);
         int row = two ? ra : rb;                              // row currently being processed
+        int left = act ? row + 1 : 0;                         // keys of the current row not yet visited
         float q[HD], acc[HD];
         auto load_q = [&](int rr) {
             const float* pq = qkv + (t0 + rr) * (size_t)(3 * d) + h * HD;
@@ -313,51 +326,48 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
 #pragma unroll
         for (int c = 0; c < HD; ++c) acc[c] = 0.f;
         float m = -INFINITY, l = 0.f;
-        int jb = 0;                                           // first key of the current block within the current row
+        const float* kp = Ks + h * HD;                        // K / V rows of the current key block
+        const float* vp = Vs + h * HD;
         for (int blk = 0; blk < nblk; ++blk) {
             if (two && blk == na) {                           // row a finished: emit it, continue with row b
                 store_o(ra, l);
-                row = rb; load_q(rb);
+                row = rb; left = rb + 1; load_q(rb);
 #pragma unroll
                 for (int c = 0; c < HD; ++c) acc[c] = 0.f;
-                m = -INFINITY; l = 0.f; jb = 0;
+                m = -INFINITY; l = 0.f;
+                kp = Ks + h * HD; vp = Vs + h * HD;
             }
-            const bool live = act && blk < na + nb;
             float sc[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int j = min(jb + jj, L - 1);
-                const float* kp = Ks + (size_t)j * ld + h * HD;
                 float dot = 0.f;
 #pragma unroll
                 for (int c = 0; c < HD; c += 4) {
-                    const float4 kv = *reinterpret_cast<const float4*>(kp + c);
+                    const float4 kv = *reinterpret_cast<const float4*>(kp + jj * ld + c);
                     dot = fmaf(q[c], kv.x, dot); dot = fmaf(q[c + 1], kv.y, dot); dot = fmaf(q[c + 2], kv.z, dot); dot = fmaf(q[c + 3], kv.w, dot);
                 }
-                sc[jj] = (live && jb + jj <= row) ? dot : -INFINITY;      // causal mask (additive -inf above the diagonal)
+                sc[jj] = (jj < left) ? dot : -INFINITY;       // causal mask (additive -inf above the diagonal) / exhausted row
             }
             const float nm = fmaxf(m, fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
-            const float nm_safe = (nm == -INFINITY) ? 0.f : nm;          // idle lanes / exhausted rows: everything masked
-            const float corr = exp2f(m - nm_safe);
+            const float nm_safe = (nm == -INFINITY) ? 0.f : nm;          // idle lanes: everything masked
+            const float corr = ex2_approx(m - nm_safe);
             float pw[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) pw[jj] = exp2f(sc[jj] - nm_safe);
+            for (int jj = 0; jj < 4; ++jj) pw[jj] = ex2_approx(sc[jj] - nm_safe);
             l = l * corr + (pw[0] + pw[1]) + (pw[2] + pw[3]);
             m = nm;
 #pragma unroll
             for (int c = 0; c < HD; ++c) acc[c] *= corr;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int j = min(jb + jj, L - 1);
-                const float* vp = Vs + (size_t)j * ld + h * HD;
 #pragma unroll
                 for (int c = 0; c < HD; c += 4) {
-                    const float4 vv = *reinterpret_cast<const float4*>(vp + c);
+                    const float4 vv = *reinterpret_cast<const float4*>(vp + jj * ld + c);
                     acc[c] = fmaf(pw[jj], vv.x, acc[c]); acc[c + 1] = fmaf(pw[jj], vv.y, acc[c + 1]);
                     acc[c + 2] = fmaf(pw[jj], vv.z, acc[c + 2]); acc[c + 3] = fmaf(pw[jj], vv.w, acc[c + 3]);
                 }
             }
-            jb += 4;
+            if (left > 0) { kp += 4 * ld; vp += 4 * ld; left -= 4; }      // stay inside the (padded) tile once the row is done
         }
         if (act) store_o(rb, l);
     }
@@ -586,7 +596,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         // attention core
         {
             const float scale = 1.0f / sqrtf((float)hd);
-            const size_t smem = sizeof(float) * 2 * (size_t)L * (d + 4);
+            const size_t smem = sizeof(float) * 2 * (size_t)(L + 4) * (d + 4);
             const bool seq_kernel = H * 32 <= 256 && (hd == 8 || hd == 16);
             prof_begin(PROF_ATTN_FWD, st);
             if (seq_kernel) {
