@@ -262,9 +262,10 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
 
 // ---- causal self-attention, one CTA per sequence (all heads) ----------------------------------------------------------------
 // K and V of the whole sequence are staged once in shared memory (coalesced loads, rows padded by 4 floats); warp h = head h.
-// Lane r owns the query rows a = r and b = L-1-r, whose causal key ranges [0,a] and [0,b] add up to L+1 keys for every
-// lane: the two rows are processed back to back in blocks of 4 keys (one online-softmax rescale per block, base-2
-// exponentials), so all active lanes run the same number of blocks and no lane idles above its diagonal.
+// Lane r owns the query rows a = r and b = L-1-r (balanced causal work); keys are visited in warp-uniform blocks of 4 so
+// that every K / V read is a broadcast float4 (1 shared-memory wavefront) shared by both rows, one online-softmax rescale
+// per block, base-2 exponentials on the MUFU.  (A back-to-back per-lane key schedule has fewer instructions but makes the
+// reads lane-divergent -- 4 wavefronts per LDS.128 -- and measured slower: shared-memory bandwidth bound.)
 __device__ __forceinline__ float ex2_approx(float x) {        // MUFU.EX2: x <= 0 here, so no overflow / denormal handling needed
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -297,79 +298,92 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
     const int half = (L + 1) / 2;
     scale *= 1.4426950408889634f;                             // softmax in base 2: exp(x) = exp2(x * log2 e)
     for (int r0 = 0; r0 < half; r0 += 32) {                  // L <= 64: one pass; L = 128: two
+        // Lane r owns rows a = r and b = L-1-r.  Keys are visited in warp-UNIFORM blocks of 4, so every K / V read is a
+        // broadcast (one shared-memory wavefront per LDS.128) shared by both rows; keys above a row's diagonal are masked.
         const int r = r0 + lane;
         const bool act = r < half;
-        const int ra = act ? r : 0, rb = act ? L - 1 - r : 0;
-        const bool two = act && (rb != ra);
-        const int na = two ? (ra + 4) / 4 : 0;                // key blocks of row a (0 when the pair degenerates to one row)
-        const int nb = act ? (rb + 4) / 4 : 0;
-        const int nblk = __reduce_max_sync(0xffffffffu, na + nb);
-        int row = two ? ra : rb;                              // row currently being processed
-        int left = act ? row + 1 : 0;                         // keys of the current row not yet visited
-        float q[HD], acc[HD];
-        auto load_q = [&](int rr) {
-            const float* pq = qkv + (t0 + rr) * (size_t)(3 * d) + h * HD;
+        const int ra = act ? r : -1, rb = act ? L - 1 - r : -1;   // -1: every key masked for idle lanes
+        float qa[HD], qb[HD], aa[HD], ab[HD];
+        {
+            const float* pa = qkv + (t0 + max(ra, 0)) * (size_t)(3 * d) + h * HD;
+            const float* pb = qkv + (t0 + max(rb, 0)) * (size_t)(3 * d) + h * HD;
 #pragma unroll
             for (int c = 0; c < HD; c += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(pq + c);
-                q[c] = v.x * scale; q[c + 1] = v.y * scale; q[c + 2] = v.z * scale; q[c + 3] = v.w * scale;
+                const float4 va = *reinterpret_cast<const float4*>(pa + c), vb = *reinterpret_cast<const float4*>(pb + c);
+                qa[c] = va.x * scale; qa[c + 1] = va.y * scale; qa[c + 2] = va.z * scale; qa[c + 3] = va.w * scale;
+                qb[c] = vb.x * scale; qb[c + 1] = vb.y * scale; qb[c + 2] = vb.z * scale; qb[c + 3] = vb.w * scale;
             }
-        };
-        auto store_o = [&](int rr, float l) {
-            const float il = 1.f / l;
-            float* po = o + (t0 + rr) * (size_t)d + h * HD;
+        }
 #pragma unroll
-            for (int c = 0; c < HD; c += 4)
-                *reinterpret_cast<float4*>(po + c) = make_float4(acc[c] * il, acc[c + 1] * il, acc[c + 2] * il, acc[c + 3] * il);
-        };
-        load_q(row);
-#pragma unroll
-        for (int c = 0; c < HD; ++c) acc[c] = 0.f;
-        float m = -INFINITY, l = 0.f;
-        const float* kp = Ks + h * HD;                        // K / V rows of the current key block
+        for (int c = 0; c < HD; ++c) { aa[c] = 0.f; ab[c] = 0.f; }
+        float ma = -INFINITY, la_ = 0.f, mb = -INFINITY, lb = 0.f;
+        const int last_a = min(half, r0 + 32) - 1;            // largest "a" row of this warp pass (warp-uniform)
+        const float* kp = Ks + h * HD;
         const float* vp = Vs + h * HD;
-        for (int blk = 0; blk < nblk; ++blk) {
-            if (two && blk == na) {                           // row a finished: emit it, continue with row b
-                store_o(ra, l);
-                row = rb; left = rb + 1; load_q(rb);
-#pragma unroll
-                for (int c = 0; c < HD; ++c) acc[c] = 0.f;
-                m = -INFINITY; l = 0.f;
-                kp = Ks + h * HD; vp = Vs + h * HD;
-            }
-            float sc[4];
+        int rem_a = ra + 1, rem_b = rb + 1;                   // keys of each row not yet visited
+        for (int j0 = 0; j0 < L; j0 += 4, kp += 4 * ld, vp += 4 * ld, rem_a -= 4, rem_b -= 4) {
+            const bool do_a = j0 <= last_a;                   // warp-uniform: the upper half of the keys only feeds rows b
+            float sa[4], sb[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                float dot = 0.f;
+                float da = 0.f, db = 0.f;
 #pragma unroll
                 for (int c = 0; c < HD; c += 4) {
                     const float4 kv = *reinterpret_cast<const float4*>(kp + jj * ld + c);
-                    dot = fmaf(q[c], kv.x, dot); dot = fmaf(q[c + 1], kv.y, dot); dot = fmaf(q[c + 2], kv.z, dot); dot = fmaf(q[c + 3], kv.w, dot);
+                    db = fmaf(qb[c], kv.x, db); db = fmaf(qb[c + 1], kv.y, db); db = fmaf(qb[c + 2], kv.z, db); db = fmaf(qb[c + 3], kv.w, db);
+                    if (do_a) { da = fmaf(qa[c], kv.x, da); da = fmaf(qa[c + 1], kv.y, da); da = fmaf(qa[c + 2], kv.z, da); da = fmaf(qa[c + 3], kv.w, da); }
                 }
-                sc[jj] = (jj < left) ? dot : -INFINITY;       // causal mask (additive -inf above the diagonal) / exhausted row
+                sa[jj] = (jj < rem_a) ? da : -INFINITY;       // causal mask (additive -inf above the diagonal)
+                sb[jj] = (jj < rem_b) ? db : -INFINITY;
             }
-            const float nm = fmaxf(m, fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])));
-            const float nm_safe = (nm == -INFINITY) ? 0.f : nm;          // idle lanes: everything masked
-            const float corr = ex2_approx(m - nm_safe);
-            float pw[4];
+            const float nmb = fmaxf(mb, fmaxf(fmaxf(sb[0], sb[1]), fmaxf(sb[2], sb[3])));
+            const float sfb = (nmb == -INFINITY) ? 0.f : nmb;
+            const float cb = ex2_approx(mb - sfb);
+            float pb_[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) pw[jj] = ex2_approx(sc[jj] - nm_safe);
-            l = l * corr + (pw[0] + pw[1]) + (pw[2] + pw[3]);
-            m = nm;
+            for (int jj = 0; jj < 4; ++jj) pb_[jj] = ex2_approx(sb[jj] - sfb);
+            lb = lb * cb + (pb_[0] + pb_[1]) + (pb_[2] + pb_[3]);
+            mb = nmb;
+            float ca = 1.f, pa_[4] = {0.f, 0.f, 0.f, 0.f};
+            if (do_a) {
+                const float nma = fmaxf(ma, fmaxf(fmaxf(sa[0], sa[1]), fmaxf(sa[2], sa[3])));
+                const float sfa = (nma == -INFINITY) ? 0.f : nma;
+                ca = ex2_approx(ma - sfa);
 #pragma unroll
-            for (int c = 0; c < HD; ++c) acc[c] *= corr;
+                for (int jj = 0; jj < 4; ++jj) pa_[jj] = ex2_approx(sa[jj] - sfa);
+                la_ = la_ * ca + (pa_[0] + pa_[1]) + (pa_[2] + pa_[3]);
+                ma = nma;
+            }
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { ab[c] *= cb; if (do_a) aa[c] *= ca; }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
 #pragma unroll
                 for (int c = 0; c < HD; c += 4) {
                     const float4 vv = *reinterpret_cast<const float4*>(vp + jj * ld + c);
-                    acc[c] = fmaf(pw[jj], vv.x, acc[c]); acc[c + 1] = fmaf(pw[jj], vv.y, acc[c + 1]);
-                    acc[c + 2] = fmaf(pw[jj], vv.z, acc[c + 2]); acc[c + 3] = fmaf(pw[jj], vv.w, acc[c + 3]);
+                    ab[c] = fmaf(pb_[jj], vv.x, ab[c]); ab[c + 1] = fmaf(pb_[jj], vv.y, ab[c + 1]);
+                    ab[c + 2] = fmaf(pb_[jj], vv.z, ab[c + 2]); ab[c + 3] = fmaf(pb_[jj], vv.w, ab[c + 3]);
+                    if (do_a) {
+                        aa[c] = fmaf(pa_[jj], vv.x, aa[c]); aa[c + 1] = fmaf(pa_[jj], vv.y, aa[c + 1]);
+                        aa[c + 2] = fmaf(pa_[jj], vv.z, aa[c + 2]); aa[c + 3] = fmaf(pa_[jj], vv.w, aa[c + 3]);
+                    }
                 }
             }
-            if (left > 0) { kp += 4 * ld; vp += 4 * ld; left -= 4; }      // stay inside the (padded) tile once the row is done
         }
-        if (act) store_o(rb, l);
+        if (act) {
+            const float ib = 1.f / lb;
+            float* ob = o + (t0 + rb) * (size_t)d + h * HD;
+#pragma unroll
+            for (int c = 0; c < HD; c += 4)
+                *reinterpret_cast<float4*>(ob + c) = make_float4(ab[c] * ib, ab[c + 1] * ib, ab[c + 2] * ib, ab[c + 3] * ib);
+            if (ra != rb) {
+                const float ia = 1.f / la_;
+                float* oa = o + (t0 + ra) * (size_t)d + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD; c += 4)
+                    *reinterpret_cast<float4*>(oa + c) = make_float4(aa[c] * ia, aa[c + 1] * ia, aa[c + 2] * ia, aa[c + 3] * ia);
+            }
+        }
     }
 }
 
