@@ -90,6 +90,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// issue only (no wait): several loads can be in flight before one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -317,11 +326,13 @@ int launch_one(const TcArgs& t, int G, cudaStream_t st) {
 // accumulators, so the global loads of tile i+1, the MMAs of tile i and the epilogue / stores of tile i-1 overlap:
 //   warps 0-7  (256 thr)  producers: fp32 activations (coalesced) -> bf16 hi/lo -> canonical K-major smem stage
 //   warp  8               one elected thread: TMA bulk load of the weight image (once), tcgen05.mma issue, tcgen05.commit
-//   warps 9-12 (128 thr)  epilogue: tcgen05.ld (thread = row) -> bias / ReLU / residual+LayerNorm -> padded smem staging ->
+//   warps 9-16 (256 thr; 9-12 only for the LayerNorm epilogue)  epilogue: tcgen05.ld (thread = row) -> bias / ReLU /
+//                          residual+LayerNorm -> padded smem staging ->
 //                          full-line coalesced global stores (a thread-per-row store would touch 32 lines per instruction)
 // =================================================================================================================================
 constexpr int PIPE_PRODUCERS = 256;
-constexpr int PIPE_THREADS = PIPE_PRODUCERS + 32 + 128;
+constexpr int PIPE_THREADS_LN = PIPE_PRODUCERS + 32 + 128;     // 4 epilogue warps (thread = full row, LayerNorm in registers)
+constexpr int PIPE_THREADS = PIPE_PRODUCERS + 32 + 256;        // 8 epilogue warps: two per TMEM lane quarter, half the columns each
 constexpr int STG_COLS = 64;                                   // columns staged per epilogue round
 constexpr int STG_ROW_BYTES = STG_COLS * 4 + 16;               // padded row -> conflict-free 16-byte stores
 constexpr int STG_BYTES = TC_M * STG_ROW_BYTES;
@@ -354,7 +365,7 @@ __device__ __forceinline__ void warp_store_rows(const uint8_t* stg_warp, float* 
 }
 
 template <int N_TILE, int K_CHUNKS, int EPI>
-__global__ void __launch_bounds__(PIPE_THREADS, 1)
+__global__ void __launch_bounds__(EPI == EPI_RES_LN ? PIPE_THREADS_LN : PIPE_THREADS, 1)
 linear_tc_pipe_kernel(TcArgs t) {
     extern __shared__ uint8_t smem_raw[];
     const LinArgs& a = t.a;
@@ -389,7 +400,7 @@ linear_tc_pipe_kernel(TcArgs t) {
         mbar_init(BAR(A_FULL), PIPE_PRODUCERS); mbar_init(BAR(A_FULL + 1), PIPE_PRODUCERS);
         mbar_init(BAR(A_EMPTY), 1); mbar_init(BAR(A_EMPTY + 1), 1);
         mbar_init(BAR(ACC_FULL), 1); mbar_init(BAR(ACC_FULL + 1), 1);
-        mbar_init(BAR(ACC_EMPTY), 128); mbar_init(BAR(ACC_EMPTY + 1), 128);
+        mbar_init(BAR(ACC_EMPTY), EPI == EPI_RES_LN ? 128 : 256); mbar_init(BAR(ACC_EMPTY + 1), EPI == EPI_RES_LN ? 128 : 256);
         mbar_init(BAR(B_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -488,7 +499,7 @@ linear_tc_pipe_kernel(TcArgs t) {
                 if (ok) umma_commit(BAR(ACC_FULL + as));       // accumulator complete
             }
         }
-    } else {
+    } else if (EPI != EPI_RES_LN || warp < 13) {
         // ------------------------------------------------ epilogue ------------------------------------------------
         const int q4 = warp & 3;                                // TMEM lane quarter this warp may access
         const int row_in_tile = q4 * 32 + lane;
@@ -521,27 +532,43 @@ linear_tc_pipe_kernel(TcArgs t) {
             const bool row_ok = r < a.Tg;
             const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * N_TILE);
             if (EPI != EPI_RES_LN) {
+                // warps 9-12 take the lower half of the columns, warps 13-16 the upper half, in rounds of 32 columns
+                constexpr int RW = 32, RW_ROW = RW * 4 + 16;
+                const int chalf = (warp - 9) >> 2;
+                uint8_t* stg_w = sStg + (warp - 9) * (32 * RW_ROW);
+                uint8_t* stg = stg_w + lane * RW_ROW;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N_TILE; c0 += STG_COLS, ++round) {
-                    uint8_t* stg_w = sStg + (round & 1) * STG_BYTES + (q4 * 32) * STG_ROW_BYTES;
-                    uint8_t* stg = stg_w + lane * STG_ROW_BYTES;
+                for (int c0 = chalf * (N_TILE / 2); c0 < (chalf + 1) * (N_TILE / 2); c0 += RW) {
+                    uint32_t ra_[16], rb_[16];
+                    tmem_ld16_issue(trow + c0, ra_);
+                    tmem_ld16_issue(trow + c0 + 16, rb_);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int cc = 0; cc < STG_COLS; cc += 16) {
-                        float v[16];
-                        tmem_ld16(trow + c0 + cc, v);
+                    for (int q = 0; q < 16; q += 4) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + q);
+                        const float4 b1 = *reinterpret_cast<const float4*>(sBias + c0 + 16 + q);
+                        float o0[4] = {__uint_as_float(ra_[q]) + b0.x, __uint_as_float(ra_[q + 1]) + b0.y, __uint_as_float(ra_[q + 2]) + b0.z, __uint_as_float(ra_[q + 3]) + b0.w};
+                        float o1[4] = {__uint_as_float(rb_[q]) + b1.x, __uint_as_float(rb_[q + 1]) + b1.y, __uint_as_float(rb_[q + 2]) + b1.z, __uint_as_float(rb_[q + 3]) + b1.w};
+                        if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) {
-                            float o[4];
+                            for (int e = 0; e < 4; ++e) { o0[e] = fmaxf(o0[e], 0.f); o1[e] = fmaxf(o1[e], 0.f); }
+                        }
+                        *reinterpret_cast<float4*>(stg + q * 4) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+                        *reinterpret_cast<float4*>(stg + (16 + q) * 4) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                    }
+                    __syncwarp();
+                    if (rows_valid > 0) {
+                        // 8 lanes cover the 128 B of one staged row, 4 rows per instruction: full-line stores
+                        float* dst0 = a.Y + (grow + m0 + q4 * 32) * (size_t)a.N + n0 + c0;
+                        const int rsub = lane >> 3, c8 = lane & 7;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                o[e] = v[q + e] + sBias[c0 + cc + q + e];
-                                if (EPI == EPI_BIAS_RELU) o[e] = fmaxf(o[e], 0.f);
-                            }
-                            *reinterpret_cast<float4*>(stg + (cc + q) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        for (int rr = 0; rr < 32; rr += 4) {
+                            const int rw = rr + rsub;
+                            const float4 v4 = *reinterpret_cast<const float4*>(stg_w + rw * RW_ROW + c8 * 16);
+                            if (rw < rows_valid) *reinterpret_cast<float4*>(dst0 + (size_t)rw * a.N + c8 * 4) = v4;
                         }
                     }
-                    if (rows_valid > 0)
-                        warp_store_rows(stg_w, a.Y + (grow + m0 + q4 * 32) * (size_t)a.N + n0 + c0, (size_t)a.N, rows_valid, lane);
+                    __syncwarp();
                 }
             } else {
                 // x_out = LayerNorm(x_res + relu(acc + b)); N_TILE == d_model, the row lives in this thread.
@@ -569,10 +596,15 @@ linear_tc_pipe_kernel(TcArgs t) {
                         __syncwarp();
                     }
                     const uint8_t* myrow = stg_w + lane * STG_ROW_BYTES;
+                    uint32_t tv[STG_COLS / 16][16];
+#pragma unroll
+                    for (int cc = 0; cc < STG_COLS; cc += 16) tmem_ld16_issue(trow + c0 + cc, tv[cc / 16]);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int cc = 0; cc < STG_COLS; cc += 16) {
                         float v[16];
-                        tmem_ld16(trow + c0 + cc, v);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(tv[cc / 16][e]);
 #pragma unroll
                         for (int q = 0; q < 16; q += 4) {
                             const float4 xr = *reinterpret_cast<const float4*>(myrow + (cc + q) * 4);
@@ -635,7 +667,7 @@ int launch_pipe(const TcArgs& t, int G, cudaStream_t st) {
     const int m_tiles = dtqn_cdiv(t.a.Tg, TC_M);
     const int gy = (t.a.N / N_TILE) * G;
     int gx = 148 / gy; if (gx < 1) gx = 1; if (gx > m_tiles) gx = m_tiles;
-    linear_tc_pipe_kernel<N_TILE, K_CHUNKS, EPI><<<dim3(gx, gy, 1), PIPE_THREADS, smem, st>>>(t);
+    linear_tc_pipe_kernel<N_TILE, K_CHUNKS, EPI><<<dim3(gx, gy, 1), EPI == EPI_RES_LN ? PIPE_THREADS_LN : PIPE_THREADS, smem, st>>>(t);
     return 0;
 }
 
