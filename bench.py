@@ -292,6 +292,15 @@ def main():
                 roof = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                         "launches_timed": v["n"], "avg_us_per_launch": 1e3 * v["ms"] / v["n"]}
+            try:
+                with open(os.path.join(ROOT, "profiles", "r1_linear_traffic.json")) as f:
+                    tj = json.load(f)
+                if nm == "linear_fwd":
+                    # DRAM bytes of the tcgen05 launches of one step (committed ncu --set full capture) / launches per step
+                    roof["traffic"] = tj["tcgen05_bytes_per_step_MB"] * 1e6 / (v["n"] / psteps)
+                    roof["traffic_note"] = "bytes per launch, averaged over the %d linear launches of a step; the 5 tcgen05 launches carry %.1f MB (ncu dram__bytes_read+write, profiles/r1_linear_traffic.json)" % (round(v["n"] / psteps), tj["tcgen05_bytes_per_step_MB"])
+            except Exception:
+                pass
             roof["per_kernel_share_of_timed_ms"] = {k: round(x["ms"] / sum(y["ms"] for y in tags.values()), 4) for k, x in tags.items()}
             roof["per_kernel_us_per_step"] = {k: round(1e3 * x["ms"] / psteps, 1) for k, x in tags.items()}
             roof["per_kernel_launches_per_step"] = {k: round(x["n"] / psteps, 1) for k, x in tags.items()}
@@ -299,6 +308,31 @@ def main():
                 if k in tags:
                     roof[k + "_GBps"] = tags[k]["work"] / (tags[k]["ms"] * 1e-3) / 1e9
         launches = int(sum(v["n"] for v in tags.values()) / max(1, psteps)) if tags else None
+
+    # ---- breakdown (single GPU): the two halves of the iteration and the pure env kernel, each as its own CUDA graph ----
+    breakdown = None
+    if world == 1:
+        def timed(graph_or_fn, n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(n):
+                graph_or_fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        tr._eps_pinned[0] = float(tr.eps.val)
+        g_act, g_train = tr.capture(tr.act_only), tr.capture(tr.train_only)
+        g_env = tr.capture(lambda: tr.env.step(mode=_lib.ACT_RANDOM))
+        for g in (g_act, g_train, g_env):
+            for _ in range(3):
+                g.replay()
+        n = max(20, min(200, args.steps))
+        ms_act, ms_train, ms_env = timed(g_act.replay, n), timed(g_train.replay, n), timed(g_env.replay, n)
+        tr.agent.num_train_steps += n + 4
+        breakdown = {"acting_half_ms": ms_act, "train_half_ms": ms_train,
+                     "train_only_grad_steps_per_sec": 1e3 / ms_train,
+                     "policy_in_loop_env_steps_per_sec_no_training": N * 1e3 / ms_act,
+                     "random_policy_env_steps_per_sec": N * 1e3 / ms_env, "env_step_plus_roll_us": 1e3 * ms_env,
+                     "env_step_GBps_algorithmic_55B": 55.0 * N / (ms_env * 1e-3) / 1e9}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -331,7 +365,7 @@ def main():
                     "steps": e2e_steps, "api": "agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
                                                 "host obs/reward/done -> agent.train -> host loss"},
             "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "breakdown": breakdown,
             "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,
         }
         print(json.dumps(line), flush=True)

@@ -84,6 +84,32 @@ class BatchedTrainer:
     def disable_graphs(self) -> None:
         self._graph = None
 
+    def capture(self, fn) -> torch.cuda.CUDAGraph:
+        """Capture ``fn()`` (kernels only, no host sync) into a CUDA graph after one warm-up call on a side stream."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def act_only(self) -> None:
+        """Acting half of an iteration: acting forward + eps-greedy + env step / append / roll."""
+        self._eps_dev.copy_(self._eps_pinned, non_blocking=True)
+        self.agent.act_and_step(self.env, 0.0, epsilon_dev=self._eps_dev)
+
+    def train_only(self) -> None:
+        """Training half of an iteration (single GPU): sample + gather + 3 forwards + TD + backward + clip + Adam."""
+        agent, rb = self.agent, self.agent.replay_buffer
+        eps, starts = rb.draw_indices(agent.batch_size)
+        rb.gather_windows(eps, starts, out=agent._win)
+        agent.forward_backward(*agent._win[:4])
+        agent.reduce_and_step()
+
     def train_iteration(self) -> None:
         """One iteration of the run.train loop body (run.py:290-298) for all envs: step, train, anneal."""
         if self._graph is not None:
