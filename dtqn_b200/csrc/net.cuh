@@ -109,3 +109,8 @@ struct LinArgs {
     float* st_save;        // (mean, rstd) [G*Tg, 2] (nullable)
 };
 
+
+// sequence-resident fused forward (net_seq.cu)
+bool seq_forward_supported(const dtqn_net_cfg& c, int L);
+int launch_seq_forward(const dtqn_net_cfg& c, const NetLayout& lay, const NetAct& act, const GroupPtrs& P, int G, int n_seq,
+                       int L, int save, float* q_out, cudaStream_t st);

@@ -549,6 +549,8 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
 // The 32 x 50-token training groups stay on fp32 CUDA cores: they are latency-bound either way (measured: no faster on
 // tensor cores) and the exact-fp32 forward keeps ReLU masks -- hence gradients -- closest to the reference's.
 static int g_tc_min_tokens = 4096;
+static int g_seq_fused = 1;
+extern "C" int dtqn_set_seq_fused(int32_t on) { g_seq_fused = on; return 0; }
 extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }
 
 extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* const* params, const void* const* packed,
@@ -594,6 +596,8 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         prof_end(PROF_EMBED, st, 2.0 * (double)T * lay.k_in * d);
         DTQN_LAUNCH_CHECK();
     }
+    if (!use_tc && q_mode == 0 && g_seq_fused && seq_forward_supported(*cfg, L))
+        return launch_seq_forward(*cfg, lay, act, P, G, n_seq, L, save, q_out, st);   // all layers + head, one launch
     const float* x_in = act.x0;
     // acting (q_mode 1) needs the final layer's output at ONE position per sequence: that layer only projects K/V for
     // every token; its query, attention row, out_proj, FFN and LayerNorms run on n_seq rows (exactly the same values).

@@ -186,6 +186,9 @@ int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, void* packed
 int dtqn_set_tc_min_tokens(int32_t n_tokens);
 /* 1 (default): persistent warp-specialised tcgen05 kernel where the weight image fits in shared memory; 0: simple one. */
 int dtqn_set_tc_pipelined(int32_t on);
+/* 1 (default): groups below the tcgen05 threshold with d_model 64, 8 heads, L <= 64 run every layer + the head in ONE
+ * sequence-resident kernel (one CTA per sequence); 0: one kernel per GEMM / attention (the general path). */
+int dtqn_set_seq_fused(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 

@@ -170,3 +170,58 @@ def test_tcgen05_forward_vs_oracle(golden_dir, env):
     for e_tc in errs.values():
         assert e_tc < Q_REL_TOL, e_tc
         assert e_tc < 2e-4, e_tc        # expected for the bf16x3 split
+
+
+@pytest.mark.parametrize("env,d,ctx,B", [("carflag", 64, 128, 6), ("memory", 128, 64, 5), ("carflag", 64, 33, 7)])
+def test_train_step_vs_oracle_other_shapes(env, d, ctx, B):
+    """Shapes the goldens do not cover (BASELINE config 5: ctx = 128; odd ctx; Memory d = 128 with 2 layers): one full
+    train step (3 forwards, TD loss, backward, clip, Adam) against the CPU oracle with fresh N(0, 0.02) x 3 weights."""
+    from dtqn_b200.agents import DtqnAgent
+    from dtqn_b200.networks import DTQN
+    from oracle import network as onet, agent as oagent
+    g = torch.Generator().manual_seed(123)
+    O, A, disc = (3, 3, False) if env == "carflag" else (10, 10, True)
+    sd = onet.init_state_dict(O, A, 8, d, 8, 2, ctx, discrete=disc, vocab_size=9 if disc else None, generator=g)
+    for k, v in sd.items():                                   # non-trivial biases / LayerNorm / position table
+        if k.endswith("attn_mask"):
+            continue
+        if k.endswith("bias") or "position_encoding" in k:
+            v.add_(torch.empty_like(v).normal_(0, 0.05, generator=g))
+        elif "layernorm" in k:
+            v.add_(torch.empty_like(v).normal_(0, 0.1, generator=g))
+        else:
+            v.mul_(3.0)
+    tgt = {k: (v + 0.01 * torch.empty_like(v).normal_(generator=g)) if not k.endswith("attn_mask") else v.clone() for k, v in sd.items()}
+
+    def mk():
+        net = DTQN(O, A, 8, 0, d, 8, 2, ctx, pos="learned", discrete=disc, vocab_sizes=9, device="cuda")
+        net.load_state_dict(sd)
+        return net
+    agent = DtqnAgent(mk, 4000, "cuda", O, max(ctx, 50) + 10, 8 if disc else -5, A, disc, batch_size=B, context_len=ctx, history=ctx)
+    agent.target_network.load_state_dict(tgt)
+    agent.strict_finite = True
+    if disc:
+        win = torch.randint(0, 9, (B, ctx + 1, O), generator=g).float()
+    else:
+        win = torch.empty(B, ctx + 1, O).uniform_(-1.1, 1.1, generator=g)
+    act = torch.randint(0, A, (B, ctx + 1), generator=g).to(torch.uint8)
+    rew = torch.randint(-1, 2, (B, ctx), generator=g).float()
+    done = (torch.rand(B, ctx, generator=g) < 0.1).to(torch.uint8)
+    agent.train_on_windows(win.cuda(), act.cuda(), rew.cuda(), done.cuda())
+    tr = oagent.TrainerOracle(sd, 8)
+    tr.target = tgt
+    conv = (lambda x: x.long()) if disc else (lambda x: x)
+    batch = (conv(win[:, :-1]), act[:, :-1, None].long(), rew[..., None], conv(win[:, 1:]), act[:, 1:, None].long(), done[..., None].bool())
+    stats, grads = tr.train_on_batch(batch)
+    st = agent.stats.cpu().numpy()
+    assert abs(st[0] - stats["loss"]) <= 1e-4 * max(1, abs(stats["loss"]))
+    assert abs(st[7] - stats["grad_norm"]) <= 2e-4 * max(1, stats["grad_norm"])
+    for got, key in zip(st[1:7], ("q_max", "q_mean", "q_min", "t_max", "t_mean", "t_min")):
+        assert abs(got - stats[key]) < 1e-4, key
+    mine = agent.policy_network.unflatten(agent.grads)
+    gmax = max(float(v.abs().max()) for v in grads.values())
+    for k, gref in grads.items():
+        err = float((mine[k].cpu() - gref).abs().max())
+        assert err <= 2e-3 * max(float(gref.abs().max()), 1e-3 * gmax), (k, err)
+    for k in tr.keys:
+        assert float((agent.policy_network.state_dict()[k].cpu() - tr.policy[k]).abs().max()) < 3e-5, k
