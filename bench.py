@@ -270,7 +270,7 @@ def main():
     if rank == 0:
         tags = {}
         names = ["linear_fwd", "attn_fwd", "env_step", "env_roll", "replay_gather", "dgrad", "wgrad", "attn_bwd", "ln_bwd",
-                 "embed", "head", "td_loss", "clip_adam", "other"]
+                 "embed", "head", "td_loss", "clip_adam", "other", "linear_tcgen05", "seq_fused_fwd"]
         for t, nm in enumerate(names):
             ms_t, n_t, w_t = C.c_double(), C.c_int64(), C.c_double()
             lib.dtqn_profile_read(t, C.byref(ms_t), C.byref(n_t), C.byref(w_t))
@@ -281,7 +281,7 @@ def main():
         dom = max(tags.items(), key=lambda kv: kv[1]["ms"]) if tags else None
         if dom is not None:
             nm, v = dom
-            tensor = nm in ("linear_fwd", "dgrad", "wgrad", "attn_fwd", "attn_bwd", "linear_tc")
+            tensor = nm in ("linear_fwd", "dgrad", "wgrad", "attn_fwd", "attn_bwd", "seq_fused_fwd")
             if tensor:
                 ach = v["work"] / (v["ms"] * 1e-3) / 1e12
                 roof = {"kernel": nm, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -295,10 +295,18 @@ def main():
             try:
                 with open(os.path.join(ROOT, "profiles", "r1_linear_traffic.json")) as f:
                     tj = json.load(f)
-                if nm == "linear_fwd":
+                if nm == "linear_tcgen05":
                     # DRAM bytes of the tcgen05 launches of one step (committed ncu --set full capture) / launches per step
                     roof["traffic"] = tj["tcgen05_bytes_per_step_MB"] * 1e6 / (v["n"] / psteps)
-                    roof["traffic_note"] = "bytes per launch, averaged over the %d linear launches of a step; the 5 tcgen05 launches carry %.1f MB (ncu dram__bytes_read+write, profiles/r1_linear_traffic.json)" % (round(v["n"] / psteps), tj["tcgen05_bytes_per_step_MB"])
+                    roof["traffic_note"] = ("bytes per launch averaged over the %d tcgen05 Linear launches of a step (ncu dram__bytes_read+write, "
+                                            "profiles/r1_linear_traffic.json); below the algorithmic bytes because part of each output is still "
+                                            "in the 126 MB L2 when the kernel ends" % round(v["n"] / psteps))
+                    # the GEMMs have K = 64..256: 24-64 FLOP per byte against a machine balance of ~220 -> HBM-bound by the roofline
+                    # model; the tensor-pipe view of the same launches (2*M*N*K per launch, x3 issued for the bf16 hi/lo split):
+                    flops = FWD_FLOP_PER_TOKEN and (2.0 * N * CTX * (64 * 192 + 64 * 64 + 64 * 256 + 256 * 64 + 64 * 128))
+                    roof["tensor_view"] = {"algorithmic_TFLOPs": flops * psteps / (v["ms"] * 1e-3) / 1e12,
+                                           "of_sustained_bf16_peak": flops * psteps / (v["ms"] * 1e-3) / 1e12 / pk["tf_sustained"],
+                                           "note": "3 MMAs issued per algorithmic MMA (bf16 hi/lo split): utilisation on algorithmic FLOPs is capped at 1/3"}
             except Exception:
                 pass
             roof["per_kernel_share_of_timed_ms"] = {k: round(x["ms"] / sum(y["ms"] for y in tags.values()), 4) for k, x in tags.items()}

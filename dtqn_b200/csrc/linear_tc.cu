@@ -141,7 +141,39 @@ struct TcArgs {
     LinArgs a;
     const uint8_t* packed[DTQN_MAX_GROUPS];
     long long pk_off;
+    TcEmbed emb;          // emb.mode: bit 0 = the A operand, bit 1 = the LayerNorm residual is the token embedding x0
 };
+
+// x0[row][c..c+3] = b_e + pos[j] + W_e obs (dtqn.py:181-199, continuous observations) recomputed on the fly, so the acting
+// forward never materialises x0: token row -> (sequence i, position j) -> context-ring row (utils/context.py window).
+__device__ __forceinline__ const float* emb_obs_row(const TcEmbed& e, int g, long long row, int& j) {
+    const int i = (int)(row / e.L);
+    j = (int)(row % e.L);
+    const dtqn_obs_src& s = e.src[g];
+    int rr = j;
+    if (s.timestep) {
+        const int ts = s.timestep[i];
+        const int n = min(s.ring_len, ts + 1);
+        rr = j < n ? (ts + 1 - n + j) % s.ring_len : -1;
+    }
+    return rr < 0 ? nullptr : s.obs + (long long)i * s.seq_stride + (long long)rr * e.O;
+}
+__device__ __forceinline__ float4 emb_x0_quad(const TcEmbed& e, const float* __restrict__ p, const float* __restrict__ sEW,
+                                              const float* __restrict__ obs, int j, int c) {
+    float ov[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ov[k] = (k < e.O) ? (obs ? __ldg(obs + k) : e.obs_mask) : 0.f;
+    const float4 pv = __ldg(reinterpret_cast<const float4*>(p + e.pos_off + (long long)j * 64 + c));
+    float o[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float acc = sEW[64 * 4 + c + q];                       // bias
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fmaf(ov[k], sEW[(c + q) * 4 + k], acc);
+        o[q] += acc;
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
 
 template <int N_TILE, int EPI>
 __global__ void __launch_bounds__(128)
@@ -382,13 +414,18 @@ linear_tc_pipe_kernel(TcArgs t) {
     uint8_t* sA = sB + ((B_BYTES + 1023) & ~1023u);            // 2 stages
     uint8_t* sStg = sA + 2 * A_STAGE_BYTES;                    // 2 staging buffers
     float* sBias = reinterpret_cast<float*>(sStg + 2 * STG_BYTES);       // bias | gamma | beta, N_TILE each
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 3 * N_TILE);    // a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full
+    float* sEW = sBias + 3 * N_TILE;                                      // obs-embedding W [64][4] (zero padded) | b [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEW + 64 * 5);           // a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     enum { A_FULL = 0, A_EMPTY = 2, ACC_FULL = 4, ACC_EMPTY = 6, B_FULL = 8 };
 
     const float* p = a.P.p[g];
+    if (t.emb.mode && tid < 64) {
+        for (int k = 0; k < 4; ++k) sEW[tid * 4 + k] = k < t.emb.O ? __ldg(p + t.emb.w_off + tid * t.emb.O + k) : 0.f;
+        sEW[64 * 4 + tid] = __ldg(p + t.emb.b_off + tid);
+    }
     if (tid < N_TILE) {
         sBias[tid] = __ldg(p + a.b_off + nt * N_TILE + tid);
         if (EPI == EPI_RES_LN) {
@@ -430,8 +467,15 @@ linear_tc_pipe_kernel(TcArgs t) {
             for (int q = 0; q < 4; ++q) {                      // 32 rows x 64 floats per pass; a warp reads 4 rows x 256 B
                 const int r = q * 32 + (tid >> 3), c = tid & 7;
                 if (m0 + r < a.Tg) {
-                    const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + kc * TC_KC + c * 8);
-                    v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
+                    if (t.emb.mode & 1) {                      // A operand = token embedding, computed here (K == 64)
+                        int j;
+                        const float* ob = emb_obs_row(t.emb, g, m0 + r, j);
+                        v[2 * q] = emb_x0_quad(t.emb, p, sEW, ob, j, c * 8);
+                        v[2 * q + 1] = emb_x0_quad(t.emb, p, sEW, ob, j, c * 8 + 4);
+                    } else {
+                        const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * a.K + kc * TC_KC + c * 8);
+                        v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
+                    }
                 } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
             }
         };
@@ -519,7 +563,13 @@ linear_tc_pipe_kernel(TcArgs t) {
                 for (int rr = 0; rr < 16; ++rr) {
                     const int rw = 2 * rr + half;
                     rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rw < rows_valid) rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4));
+                    if (rw < rows_valid) {
+                        if (t.emb.mode & 2) {                  // residual = token embedding x0, recomputed (never stored)
+                            int j;
+                            const float* ob = emb_obs_row(t.emb, g, (long long)m0 + q4 * 32 + rw, j);
+                            rv[rr] = emb_x0_quad(t.emb, p, sEW, ob, j, c16 * 4);
+                        } else rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * N_TILE + c16 * 4));
+                    }
                 }
 #pragma unroll
                 for (int rr = 0; rr < 16; ++rr)
@@ -656,7 +706,7 @@ linear_tc_pipe_kernel(TcArgs t) {
 template <int N_TILE, int K_CHUNKS, int EPI>
 int launch_pipe(const TcArgs& t, int G, cudaStream_t st) {
     constexpr size_t B_BYTES = (size_t)N_TILE * TC_KC * 4 * K_CHUNKS;
-    constexpr size_t smem = 1024 + ((B_BYTES + 1023) & ~(size_t)1023) + 2 * A_STAGE_BYTES + 2 * STG_BYTES + 3 * N_TILE * 4 + 128;
+    constexpr size_t smem = 1024 + ((B_BYTES + 1023) & ~(size_t)1023) + 2 * A_STAGE_BYTES + 2 * STG_BYTES + 3 * N_TILE * 4 + 64 * 5 * 4 + 128;
     static_assert(smem <= 227 * 1024, "pipelined tcgen05 Linear: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
@@ -695,6 +745,7 @@ int launch_pipe_dispatch(const TcArgs& t, int G, int nt, cudaStream_t st, bool& 
 
 static int g_tc_pipelined = 1;
 extern "C" int dtqn_set_tc_pipelined(int32_t on) { g_tc_pipelined = on; return 0; }
+bool tc_pipelined_enabled() { return g_tc_pipelined != 0; }
 
 int tc_ntile(int N) {
     switch (N) {
@@ -725,22 +776,28 @@ int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab)
     return 0;
 }
 
-int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st) {
+int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st,
+                     const TcEmbed* emb) {
     TcArgs t{};
     t.a = a; t.pk_off = pk_off;
+    if (emb) t.emb = *emb;
     for (int g = 0; g < G; ++g) t.packed[g] = packed[g];
     const int nt = tc_ntile(a.N);
     if (!nt || a.K % TC_KC) return DTQN_E_UNSUPPORTED;
     int rc = DTQN_E_UNSUPPORTED;
-    prof_begin(PROF_LINEAR, st);
+    // HBM roofline of this launch: activations read once (K floats / token), output written once (N), the residual read
+    // by the LayerNorm epilogue (N), the weight image once
+    const double tc_bytes = 4.0 * ((double)a.Tg * G * (a.K + a.N + (epi == EPI_RES_LN ? a.N : 0)) + (double)a.N * a.K);
+    prof_begin(PROF_LINEAR_TC, st);
     bool handled = false;
+    if (emb && emb->mode && !g_tc_pipelined) return DTQN_E_UNSUPPORTED;   // only the pipelined kernel embeds on the fly
     if (g_tc_pipelined) {
         if (epi == EPI_RES_LN) rc = launch_pipe_dispatch<EPI_RES_LN>(t, G, nt, st, handled);
         else if (epi == EPI_BIAS) rc = launch_pipe_dispatch<EPI_BIAS>(t, G, nt, st, handled);
         else rc = launch_pipe_dispatch<EPI_BIAS_RELU>(t, G, nt, st, handled);
     }
     if (handled) {
-        prof_end(PROF_LINEAR, st, 2.0 * (double)a.Tg * G * a.N * a.K);
+        prof_end(PROF_LINEAR_TC, st, tc_bytes);
         if (rc) return rc;
         DTQN_LAUNCH_CHECK();
         return 0;
@@ -759,7 +816,7 @@ int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* pac
         else if (nt == 192) rc = launch_one<192, EPI_BIAS_RELU>(t, G, st);
         else rc = launch_one<256, EPI_BIAS_RELU>(t, G, st);
     }
-    prof_end(PROF_LINEAR, st, 2.0 * (double)a.Tg * G * a.N * a.K);
+    prof_end(PROF_LINEAR_TC, st, tc_bytes);
     if (rc) return rc;
     DTQN_LAUNCH_CHECK();
     return 0;

@@ -9,6 +9,17 @@ struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1]; int n; long long to
 // of in_proj (index 4*n_layers + 1 + 2*i, + 1)
 enum { TC_W_IN = 0, TC_W_OUT = 1, TC_W_F1 = 2, TC_W_F2 = 3 };
 
+// token embedding recomputed inside the tcgen05 kernel (continuous observations, d_model = 64)
+struct TcEmbed {
+    int mode;                         // 0 off; bit 0: A operand; bit 1: LayerNorm residual
+    int L, O;
+    float obs_mask;
+    long long w_off, b_off, pos_off;  // offsets into the flat parameters
+    dtqn_obs_src src[DTQN_MAX_GROUPS];
+};
+
+bool tc_pipelined_enabled();
 int tc_ntile(int N);
 int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab);
-int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st);
+int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st,
+                     const TcEmbed* emb = nullptr);

@@ -550,6 +550,8 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
 // tensor cores) and the exact-fp32 forward keeps ReLU masks -- hence gradients -- closest to the reference's.
 static int g_tc_min_tokens = 4096;
 static int g_seq_fused = 1;
+static int g_tc_fuse_embed = 1;
+extern "C" int dtqn_set_tc_fuse_embed(int32_t on) { g_tc_fuse_embed = on; return 0; }
 extern "C" int dtqn_set_seq_fused(int32_t on) { g_seq_fused = on; return 0; }
 extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }
 
@@ -577,13 +579,25 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     }
     TcPackTable tab{};
     if (use_tc) tc_pack_table(*cfg, lay, tab);
-    auto linear = [&](const LinArgs& a, int epi, int tab_idx) -> int {
-        if (use_tc) return launch_linear_tc(a, epi, G, pk, tab.e[tab_idx].pk_off, st);
+    // acting forward on the tensor-core path with continuous observations: the token embedding x0 is recomputed inside
+    // the in_proj producer and the out_proj LayerNorm epilogue of layer 0 and never written to HBM
+    const bool fuse_embed = use_tc && g_tc_fuse_embed && tc_pipelined_enabled() && q_mode == 1 && !cfg->discrete && cfg->obs_dim <= 4 && d == 64 &&
+                            cfg->n_layers >= 2 && L >= 3 && H * 32 <= 256;
+    TcEmbed emb{};
+    if (fuse_embed) {
+        emb.L = L; emb.O = cfg->obs_dim; emb.obs_mask = -5.0f; emb.w_off = lay.emb_w; emb.b_off = lay.emb_b; emb.pos_off = lay.pos;
+        for (int g = 0; g < G; ++g) emb.src[g] = src[g];
+    }
+    auto linear = [&](const LinArgs& a, int epi, int tab_idx, int emb_mode = 0) -> int {
+        if (use_tc) {
+            if (emb_mode) { emb.mode = emb_mode; return launch_linear_tc(a, epi, G, pk, tab.e[tab_idx].pk_off, st, &emb); }
+            return launch_linear_tc(a, epi, G, pk, tab.e[tab_idx].pk_off, st);
+        }
         if (epi == EPI_BIAS) return launch_linear<EPI_BIAS>(a, G, d, st);
         if (epi == EPI_BIAS_RELU) return launch_linear<EPI_BIAS_RELU>(a, G, d, st);
         return launch_linear<EPI_RES_LN>(a, G, d, st);
     };
-    {
+    if (!fuse_embed) {
         prof_begin(PROF_EMBED, st);
         if (!cfg->discrete && cfg->obs_dim <= 16) {
             if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
@@ -610,7 +624,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.P = P; a.Tg = (int)Tg;
         // in_proj
         a.X = x_in; a.Y = la.qkv; a.w_off = lo.in_w; a.b_off = lo.in_b; a.N = 3 * d; a.K = d;
-        if ((rc = linear(a, EPI_BIAS, 4 * li + TC_W_IN))) return rc;
+        if ((rc = linear(a, EPI_BIAS, 4 * li + TC_W_IN, (fuse_embed && li == 0) ? 1 : 0))) return rc;
         // attention core
         {
             const float scale = 1.0f / sqrtf((float)hd);
@@ -641,7 +655,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.X = la.o; a.Y = la.x1; a.w_off = lo.out_w; a.b_off = lo.out_b; a.N = d; a.K = d;
         a.R = x_in; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b;
         a.r_save = save ? la.r1 : nullptr; a.st_save = save ? la.st1 : nullptr;
-        if ((rc = linear(a, EPI_RES_LN, 4 * li + TC_W_OUT))) return rc;
+        if ((rc = linear(a, EPI_RES_LN, 4 * li + TC_W_OUT, (fuse_embed && li == 0) ? 2 : 0))) return rc;
         // ffn.0 + relu
         a.X = la.x1; a.Y = la.h; a.w_off = lo.f1_w; a.b_off = lo.f1_b; a.N = 4 * d; a.K = d;
         if ((rc = linear(a, EPI_BIAS_RELU, 4 * li + TC_W_F1))) return rc;

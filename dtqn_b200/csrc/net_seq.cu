@@ -344,9 +344,9 @@ int launch_seq_forward(const dtqn_net_cfg& c, const NetLayout& lay, const NetAct
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    prof_begin(PROF_LINEAR, st);
+    prof_begin(PROF_SEQ_FWD, st);
     seq_forward_kernel<<<G * n_seq, SQ_THREADS, sizeof(SeqSmem), st>>>(a);
-    prof_end(PROF_LINEAR, st, 2.0 * (double)G * n_seq * L * (c.n_layers * 12.0 * SQ_D * SQ_D + SQ_D * SQ_D + SQ_D * c.num_actions));
+    prof_end(PROF_SEQ_FWD, st, 2.0 * (double)G * n_seq * L * (c.n_layers * 12.0 * SQ_D * SQ_D + SQ_D * SQ_D + SQ_D * c.num_actions));
     DTQN_LAUNCH_CHECK();
     return 0;
 }

@@ -19,7 +19,9 @@ enum ProfTag {
     PROF_TD = 11,
     PROF_ADAM = 12,
     PROF_OTHER = 13,
-    PROF_NTAGS = 14
+    PROF_LINEAR_TC = 14, // tcgen05 Linear launches; work = algorithmic BYTES (fp32 activations in + out, residual, weights)
+    PROF_SEQ_FWD = 15,   // sequence-resident fused forward (all layers + head); work = FLOPs
+    PROF_NTAGS = 16
 };
 
 extern bool g_prof_on;

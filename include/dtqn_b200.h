@@ -189,6 +189,9 @@ int dtqn_set_tc_pipelined(int32_t on);
 /* 1 (default): groups below the tcgen05 threshold with d_model 64, 8 heads, L <= 64 run every layer + the head in ONE
  * sequence-resident kernel (one CTA per sequence); 0: one kernel per GEMM / attention (the general path). */
 int dtqn_set_seq_fused(int32_t on);
+/* 1 (default): the acting forward recomputes the token embedding inside the tcgen05 in_proj / out_proj kernels of layer 0
+ * (continuous observations) instead of materialising it; 0: separate embed kernel. */
+int dtqn_set_tc_fuse_embed(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 
@@ -224,7 +227,8 @@ int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
  * When enabled, every launch of a tagged kernel is bracketed by CUDA events on its stream.  dtqn_profile_read
  * synchronises and returns the summed duration, launch count and algorithmic work (FLOPs or bytes) of one tag.
  * Tags: 0 linear-fwd GEMM, 1 attention-fwd, 2 env-step, 3 env-roll, 4 replay-gather, 5 dgrad, 6 wgrad, 7 attention-bwd,
- * 8 layernorm-bwd, 9 embed, 10 head, 11 td-loss, 12 clip+adam, 13 other.  Process-global, not thread-safe. */
+ * 8 layernorm-bwd, 9 embed, 10 head, 11 td-loss, 12 clip+adam, 13 other, 14 tcgen05 Linear (work = algorithmic bytes),
+ * 15 sequence-resident fused forward.  Process-global, not thread-safe. */
 int dtqn_profile_enable(int32_t on);
 int dtqn_profile_read(int32_t tag, double* total_ms, int64_t* launches, double* total_work);
 

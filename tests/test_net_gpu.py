@@ -225,3 +225,26 @@ def test_train_step_vs_oracle_other_shapes(env, d, ctx, B):
         assert err <= 2e-3 * max(float(gref.abs().max()), 1e-3 * gmax), (k, err)
     for k in tr.keys:
         assert float((agent.policy_network.state_dict()[k].cpu() - tr.policy[k]).abs().max()) < 3e-5, k
+
+
+def test_acting_forward_embed_fusion_matches_unfused(golden_dir):
+    """Acting forward with the token embedding recomputed inside the tcgen05 kernels == the same forward with a separate
+    embed kernel (bitwise-close: same arithmetic, different place), for 4096 contexts of mixed lengths."""
+    from dtqn_b200 import _lib
+    from dtqn_b200.agents import DtqnAgent
+    z = np.load(os.path.join(golden_dir, "acting_carflag.npz"))
+    d, layers, ctx, heads = [int(v) for v in z["meta"]]
+    K = 1024
+    agent = DtqnAgent(lambda: _make_net(z, "policy/", "carflag"), 200 * K * 2, "cuda", 3, 200, -5, 3, False, context_len=ctx, n_envs=K)
+    g = torch.Generator().manual_seed(9)
+    cx = agent.context
+    cx.obs.copy_(torch.trunc(torch.empty(K, ctx, 3).uniform_(-1.5, 1.5, generator=g)))
+    cx.timestep_t.copy_(torch.randint(0, 180, (K,), generator=g).int())
+    _lib.lib.dtqn_set_tc_fuse_embed(1)
+    q_fused = agent.q_last_batched().clone()
+    _lib.lib.dtqn_set_tc_fuse_embed(0)
+    q_plain = agent.q_last_batched().clone()
+    _lib.lib.dtqn_set_tc_fuse_embed(1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(q_fused).all()
+    assert (q_fused - q_plain).abs().max().item() <= 1e-5 * max(1.0, q_plain.abs().max().item())
