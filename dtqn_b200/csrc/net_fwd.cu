@@ -550,7 +550,7 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
 // tensor cores) and the exact-fp32 forward keeps ReLU masks -- hence gradients -- closest to the reference's.
 static int g_tc_min_tokens = 4096;
 static int g_seq_fused = 1;
-static int g_tc_fuse_embed = 1;
+static int g_tc_fuse_embed = 0;   // measured slower (dependent timestep -> obs -> pos loads stall the producers): off by default
 extern "C" int dtqn_set_tc_fuse_embed(int32_t on) { g_tc_fuse_embed = on; return 0; }
 extern "C" int dtqn_set_seq_fused(int32_t on) { g_seq_fused = on; return 0; }
 extern "C" int dtqn_set_tc_min_tokens(int32_t n) { g_tc_min_tokens = n; return 0; }

@@ -189,8 +189,8 @@ int dtqn_set_tc_pipelined(int32_t on);
 /* 1 (default): groups below the tcgen05 threshold with d_model 64, 8 heads, L <= 64 run every layer + the head in ONE
  * sequence-resident kernel (one CTA per sequence); 0: one kernel per GEMM / attention (the general path). */
 int dtqn_set_seq_fused(int32_t on);
-/* 1 (default): the acting forward recomputes the token embedding inside the tcgen05 in_proj / out_proj kernels of layer 0
- * (continuous observations) instead of materialising it; 0: separate embed kernel. */
+/* 1: the acting forward recomputes the token embedding inside the tcgen05 in_proj / out_proj kernels of layer 0
+ * (continuous observations) instead of materialising it; 0 (default, measured faster): separate embed kernel. */
 int dtqn_set_tc_fuse_embed(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);

@@ -244,7 +244,6 @@ def test_acting_forward_embed_fusion_matches_unfused(golden_dir):
     q_fused = agent.q_last_batched().clone()
     _lib.lib.dtqn_set_tc_fuse_embed(0)
     q_plain = agent.q_last_batched().clone()
-    _lib.lib.dtqn_set_tc_fuse_embed(1)
     torch.cuda.synchronize()
     assert torch.isfinite(q_fused).all()
     assert (q_fused - q_plain).abs().max().item() <= 1e-5 * max(1.0, q_plain.abs().max().item())
