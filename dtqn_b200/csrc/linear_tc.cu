@@ -703,6 +703,302 @@ linear_tc_pipe_kernel(TcArgs t) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+
+// =================================================================================================================================
+// Fused position-wise FFN on tcgen05 (d_model = 64, hidden 256):  x2 = LayerNorm(x1 + relu(W2 relu(W1 x1 + b1) + b2))
+// (transformer.py:37-42,74-77).  The [128 x 256] hidden tile never leaves the SM: MMA1 writes it to TMEM, the "hidden"
+// epilogue warps read it back 64 columns at a time, apply bias + ReLU, split to bf16 hi/lo and store it as the K-major A
+// operand of MMA2, whose [128 x 64] accumulator is drained by the LayerNorm epilogue warps.  Per token this moves
+// 64 floats in + 64 residual + 64 out instead of 64 + 256 + 256 + 64 + 64 (the unfused ffn.0 / ffn.2 pair): 4x less HBM traffic.
+//   warps 0-7   producers: x1 tile fp32 -> bf16 hi/lo -> A1 (one stage; two register sets keep the next tile's loads in flight)
+//   warp  8     elected lane: TMA W1 image once (64 KB), W2 k-chunks through a 2-stage ring (16 KB each), all MMAs + commits
+//   warps 9-12  hidden epilogue:  acc1[c] -> +b1 -> ReLU -> hi/lo -> A2 (K-major) ; signals A2_FULL per 64-column chunk
+//   warps 13-16 LayerNorm epilogue: acc2 -> +b2 -> ReLU -> +x1 -> LN -> staged, full-line stores
+// TMEM: acc1 = 256 columns (4 chunks), acc2 = 2 x 64 columns (double buffered across tiles).
+// =================================================================================================================================
+constexpr int FFN_THREADS = PIPE_PRODUCERS + 32 + 128 + 128;
+
+struct FfnArgs {
+    const float* X;            // x1 [G*Tg, 64]  (input and LayerNorm residual)
+    float* Y;                  // x2 [G*Tg, 64]
+    GroupPtrs P;
+    const uint8_t* packed[DTQN_MAX_GROUPS];
+    long long pk_w1, pk_w2;    // byte offsets of the two weight images in the packed buffer
+    long long b1_off, b2_off, gamma_off, beta_off;
+    int Tg;
+};
+
+__global__ void __launch_bounds__(FFN_THREADS, 1)
+ffn_tc_kernel(FfnArgs t) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int D = 64, HID = 256, NCH = HID / 64;
+    constexpr uint32_t W1_BYTES = HID * TC_KC * 4;             // hi + lo of the whole [256 x 64] image
+    constexpr uint32_t W1_HALF = HID * TC_KC * 2;
+    constexpr uint32_t W2C_BYTES = D * TC_KC * 4;              // one k-chunk of W2 [64 x 64] hi + lo
+    constexpr uint32_t W2C_HALF = D * TC_KC * 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW1 = base;
+    uint8_t* sW2 = sW1 + W1_BYTES;                             // 2 stages
+    uint8_t* sA1 = sW2 + 2 * W2C_BYTES;
+    uint8_t* sA2 = sA1 + A_STAGE_BYTES;
+    uint8_t* sStg = sA2 + A_STAGE_BYTES;                       // residual rows, then output rows (same region)
+    float* sB1 = reinterpret_cast<float*>(sStg + STG_BYTES);   // b1[256] | b2[64] | gamma[64] | beta[64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + HID + 3 * D);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    enum { W1_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, ACC1_FULL = 3, ACC1_EMPTY = 4, A2_FULL = 5, A2_EMPTY = 6,
+           W2_FULL = 7 /*+s*/, W2_EMPTY = 9 /*+s*/, ACC2_FULL = 11 /*+as*/, ACC2_EMPTY = 13 /*+as*/ };
+
+    const float* p = t.P.p[g];
+    for (int e = tid; e < HID; e += FFN_THREADS) sB1[e] = __ldg(p + t.b1_off + e);
+    if (tid < D) {
+        sB1[HID + tid] = __ldg(p + t.b2_off + tid);
+        sB1[HID + D + tid] = __ldg(p + t.gamma_off + tid);
+        sB1[HID + 2 * D + tid] = __ldg(p + t.beta_off + tid);
+    }
+    if (tid == 0) {
+        mbar_init(BAR(W1_FULL), 1);
+        mbar_init(BAR(A1_FULL), PIPE_PRODUCERS); mbar_init(BAR(A1_EMPTY), 1);
+        mbar_init(BAR(ACC1_FULL), 1); mbar_init(BAR(ACC1_EMPTY), 128);
+        mbar_init(BAR(A2_FULL), 128); mbar_init(BAR(A2_EMPTY), 1);
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(BAR(W2_FULL + k), 1); mbar_init(BAR(W2_EMPTY + k), 1);
+            mbar_init(BAR(ACC2_FULL + k), 1); mbar_init(BAR(ACC2_EMPTY + k), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tm_acc1 = tmem, tm_acc2 = tmem + 256;       // acc1: columns [0,256); acc2[as]: [256 + 64 as, +64)
+
+    const size_t grow = (size_t)g * t.Tg;
+    const int m_tiles = (t.Tg + TC_M - 1) / TC_M;
+    const int my_tiles = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < 8) {
+        // ------------------------------------------------ producers ------------------------------------------------
+        const float* X = t.X + grow * D;
+        auto issue = [&](int i, float4 (&v)[8]) {
+            const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + (tid >> 3), c = tid & 7;
+                if (m0 + r < t.Tg) {
+                    const float4* src = reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * D + c * 8);
+                    v[2 * q] = __ldg(src); v[2 * q + 1] = __ldg(src + 1);
+                } else { v[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * q + 1] = v[2 * q]; }
+            }
+        };
+        auto finish = [&](int i, float4 (&v)[8]) -> bool {
+            if (i >= 1 && !mbar_wait(BAR(A1_EMPTY), (uint32_t)((i - 1) & 1))) return false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + (tid >> 3), c = tid & 7;
+                const float x[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(sA1 + c * A_CHUNK_STRIDE + r * 16) = hi;
+                *reinterpret_cast<uint4*>(sA1 + A_HALF_BYTES + c * A_CHUNK_STRIDE + r * 16) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(BAR(A1_FULL));
+            return true;
+        };
+        float4 va[8], vb[8];
+        if (my_tiles > 0) issue(0, va);
+        bool okp = true;
+        for (int i = 0; i < my_tiles && okp; i += 2) {
+            if (i + 1 < my_tiles) issue(i + 1, vb);
+            okp = finish(i, va);
+            if (i + 2 < my_tiles) issue(i + 2, va);
+            if (okp && i + 1 < my_tiles) okp = finish(i + 1, vb);
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------ MMA issuer ------------------------------------------------
+        if (lane == 0) {
+            const uint8_t* w1img = t.packed[g] + t.pk_w1;
+            const uint8_t* w2img = t.packed[g] + t.pk_w2;
+            mbar_expect_tx(BAR(W1_FULL), W1_BYTES);
+            bulk_g2s(smem_u32(sW1), w1img, 32768u, BAR(W1_FULL));
+            bulk_g2s(smem_u32(sW1) + 32768u, w1img + 32768, 32768u, BAR(W1_FULL));
+            const int n_total = my_tiles * NCH;
+            auto load_w2 = [&](int n) {                        // chunk n = 4 i + c -> ring stage n & 1
+                const int s_ = n & 1, c = n % NCH;
+                mbar_expect_tx(BAR(W2_FULL + s_), W2C_BYTES);
+                bulk_g2s(smem_u32(sW2) + (uint32_t)s_ * W2C_BYTES, w2img + (size_t)c * W2C_BYTES, W2C_BYTES, BAR(W2_FULL + s_));
+            };
+            if (n_total > 0) load_w2(0);
+            if (n_total > 1) load_w2(1);
+            bool ok = mbar_wait(BAR(W1_FULL), 0);
+            const uint32_t idesc = umma_idesc(TC_M, 64);
+            const uint32_t sA1_u = smem_u32(sA1), sA2_u = smem_u32(sA2), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
+            for (int i = 0; i < my_tiles && ok; ++i) {
+                const int as = i & 1;
+                ok = mbar_wait(BAR(A1_FULL), (uint32_t)(i & 1));
+                if (ok && i >= 1) ok = mbar_wait(BAR(ACC1_EMPTY), (uint32_t)((i - 1) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                // MMA1: hidden[128 x 256] = x1[128 x 64] W1^T, as four N = 64 column chunks of the resident W1 image
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+                        const uint64_t a_hi = umma_desc(sA1_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t a_lo = umma_desc(sA1_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint32_t boff = (uint32_t)(k16 * 2 * (HID * 16) + c * 64 * 16);
+                        const uint64_t b_hi = umma_desc(sW1_u + boff, HID * 16, 128);
+                        const uint64_t b_lo = umma_desc(sW1_u + W1_HALF + boff, HID * 16, 128);
+                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_hi, idesc, k16 ? 1u : 0u);
+                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_lo, idesc, 1u);
+                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_lo, b_hi, idesc, 1u);
+                    }
+                }
+                umma_commit(BAR(A1_EMPTY));
+                umma_commit(BAR(ACC1_FULL));
+                // MMA2: out[128 x 64] += relu(hidden chunk c)[128 x 64] W2[:, chunk c]^T
+                for (int c = 0; c < NCH && ok; ++c) {
+                    const int n = i * NCH + c, s_ = n & 1, m = n >> 1;
+                    ok = mbar_wait(BAR(W2_FULL + s_), (uint32_t)(m & 1));
+                    if (ok) ok = mbar_wait(BAR(A2_FULL), (uint32_t)(n & 1));
+                    if (ok && c == 0 && i >= 2) ok = mbar_wait(BAR(ACC2_EMPTY + as), (uint32_t)(((i >> 1) - 1) & 1));
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t wb = sW2_u + (uint32_t)s_ * W2C_BYTES;
+#pragma unroll
+                    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+                        const uint64_t a_hi = umma_desc(sA2_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t a_lo = umma_desc(sA2_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t b_hi = umma_desc(wb + k16 * 2 * (D * 16), D * 16, 128);
+                        const uint64_t b_lo = umma_desc(wb + W2C_HALF + k16 * 2 * (D * 16), D * 16, 128);
+                        umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_hi, b_hi, idesc, (c | k16) ? 1u : 0u);
+                        umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_hi, b_lo, idesc, 1u);
+                        umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_lo, b_hi, idesc, 1u);
+                    }
+                    umma_commit(BAR(A2_EMPTY));
+                    umma_commit(BAR(W2_EMPTY + s_));
+                    if (n + 2 < n_total) {                     // refill this ring stage once its MMAs have retired
+                        ok = mbar_wait(BAR(W2_EMPTY + s_), (uint32_t)(m & 1));
+                        if (ok) load_w2(n + 2);
+                    }
+                }
+                if (ok) umma_commit(BAR(ACC2_FULL + as));
+            }
+        }
+    } else if (warp < 13) {
+        // ------------------------------------------------ hidden epilogue ------------------------------------------------
+        const int q4 = warp & 3, row = q4 * 32 + lane;
+        for (int i = 0; i < my_tiles; ++i) {
+            if (!mbar_wait(BAR(ACC1_FULL), (uint32_t)(i & 1))) break;
+            tc_fence_after();
+            bool ok = true;
+            for (int c = 0; c < NCH && ok; ++c) {
+                const int n = i * NCH + c;
+                uint32_t tv[4][16];
+                const uint32_t trow = tm_acc1 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 64);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) tmem_ld16_issue(trow + cc * 16, tv[cc]);
+                tmem_ld_wait();
+                if (n >= 1) ok = mbar_wait(BAR(A2_EMPTY), (uint32_t)((n - 1) & 1));   // MMA2 of the previous chunk done with A2
+                if (!ok) break;
+#pragma unroll
+                for (int sub = 0; sub < 8; ++sub) {
+                    float x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        x[e] = fmaxf(__uint_as_float(tv[sub >> 1][(sub & 1) * 8 + e]) + sB1[c * 64 + sub * 8 + e], 0.f);
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    *reinterpret_cast<uint4*>(sA2 + sub * A_CHUNK_STRIDE + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(sA2 + A_HALF_BYTES + sub * A_CHUNK_STRIDE + row * 16) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(BAR(A2_FULL));
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC1_EMPTY));
+            if (!ok) break;
+        }
+    } else {
+        // ------------------------------------------------ LayerNorm epilogue ------------------------------------------------
+        const int q4 = warp & 3, row_in_tile = q4 * 32 + lane;
+        const float* sB2 = sB1 + HID; const float* sG = sB2 + D; const float* sBe = sG + D;
+        uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
+        const int half = lane >> 4, c16 = lane & 15;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int as = i & 1;
+            const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
+            const int rows_valid = min(32, t.Tg - (m0 + q4 * 32));
+            {   // residual rows of this warp -> staging (full-line loads, all in flight)
+                const float* src0 = t.X + (grow + m0 + q4 * 32) * (size_t)D;
+                float4 rv[16];
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int rw = 2 * rr + half;
+                    rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rw < rows_valid) rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * D + c16 * 4));
+                }
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr)
+                    *reinterpret_cast<float4*>(stg_w + (2 * rr + half) * STG_ROW_BYTES + c16 * 16) = rv[rr];
+                __syncwarp();
+            }
+            if (!mbar_wait(BAR(ACC2_FULL + as), (uint32_t)((i >> 1) & 1))) break;
+            tc_fence_after();
+            const uint32_t trow = tm_acc2 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 64);
+            uint32_t tv[4][16];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) tmem_ld16_issue(trow + cc * 16, tv[cc]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(BAR(ACC2_EMPTY + as));                 // accumulator copied to registers: MMA2 of tile i+2 may start
+            float u[D];
+            float s = 0.f;
+            const uint8_t* myrow = stg_w + lane * STG_ROW_BYTES;
+#pragma unroll
+            for (int q = 0; q < D; q += 4) {
+                const float4 xr = *reinterpret_cast<const float4*>(myrow + q * 4);
+                const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    u[q + e] = xv[e] + fmaxf(__uint_as_float(tv[(q + e) >> 4][(q + e) & 15]) + sB2[q + e], 0.f);
+                    s += u[q + e];
+                }
+            }
+            const float mean = s * (1.f / D);
+            float vs = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) { const float dl = u[j] - mean; vs = fmaf(dl, dl, vs); }
+            const float rstd = 1.0f / sqrtf(vs * (1.f / D) + 1e-5f);
+            __syncwarp();                                      // every lane has consumed its residual row
+            uint8_t* mystg = stg_w + lane * STG_ROW_BYTES;
+#pragma unroll
+            for (int q = 0; q < D; q += 4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = (u[q + e] - mean) * rstd * sG[q + e] + sBe[q + e];
+                *reinterpret_cast<float4*>(mystg + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (rows_valid > 0)
+                warp_store_rows(stg_w, t.Y + (grow + m0 + q4 * 32) * (size_t)D, (size_t)D, rows_valid, lane);
+            else { __syncwarp(); __syncwarp(); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 template <int N_TILE, int K_CHUNKS, int EPI>
 int launch_pipe(const TcArgs& t, int G, cudaStream_t st) {
     constexpr size_t B_BYTES = (size_t)N_TILE * TC_KC * 4 * K_CHUNKS;
@@ -746,6 +1042,37 @@ int launch_pipe_dispatch(const TcArgs& t, int G, int nt, cudaStream_t st, bool& 
 static int g_tc_pipelined = 1;
 extern "C" int dtqn_set_tc_pipelined(int32_t on) { g_tc_pipelined = on; return 0; }
 bool tc_pipelined_enabled() { return g_tc_pipelined != 0; }
+
+
+static int g_tc_fuse_ffn = 1;
+extern "C" int dtqn_set_tc_fuse_ffn(int32_t on) { g_tc_fuse_ffn = on; return 0; }
+bool tc_ffn_fused_enabled() { return g_tc_fuse_ffn != 0 && g_tc_pipelined != 0; }
+
+int launch_ffn_tc(const float* X, float* Y, const GroupPtrs& P, int G, const uint8_t* const* packed, long long pk_w1,
+                  long long pk_w2, long long b1_off, long long b2_off, long long gamma_off, long long beta_off, int Tg,
+                  cudaStream_t st) {
+    FfnArgs t{};
+    t.X = X; t.Y = Y; t.P = P; t.pk_w1 = pk_w1; t.pk_w2 = pk_w2; t.b1_off = b1_off; t.b2_off = b2_off;
+    t.gamma_off = gamma_off; t.beta_off = beta_off; t.Tg = Tg;
+    for (int g = 0; g < G; ++g) t.packed[g] = packed[g];
+    constexpr size_t smem = 1024 + 256 * TC_KC * 4 + 2 * 64 * TC_KC * 4 + 2 * A_STAGE_BYTES + STG_BYTES + (256 + 3 * 64) * 4 + 256;
+    static_assert(smem <= 227 * 1024, "fused FFN: shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int m_tiles = dtqn_cdiv(Tg, TC_M);
+    int gx = 148 / G; if (gx < 1) gx = 1; if (gx > m_tiles) gx = m_tiles;
+    // HBM roofline of the fused pair: x1 read as operand and as residual, x2 written, both weight images once
+    const double bytes = 4.0 * ((double)Tg * G * (64 + 64 + 64) + 2.0 * 256 * 64);
+    prof_begin(PROF_LINEAR_TC, st);
+    ffn_tc_kernel<<<dim3(gx, G, 1), FFN_THREADS, smem, st>>>(t);
+    prof_end(PROF_LINEAR_TC, st, bytes);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
 
 int tc_ntile(int N) {
     switch (N) {

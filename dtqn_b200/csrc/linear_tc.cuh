@@ -19,6 +19,10 @@ struct TcEmbed {
 };
 
 bool tc_pipelined_enabled();
+bool tc_ffn_fused_enabled();
+int launch_ffn_tc(const float* X, float* Y, const GroupPtrs& P, int G, const uint8_t* const* packed, long long pk_w1,
+                  long long pk_w2, long long b1_off, long long b2_off, long long gamma_off, long long beta_off, int Tg,
+                  cudaStream_t st);
 int tc_ntile(int N);
 int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab);
 int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st,

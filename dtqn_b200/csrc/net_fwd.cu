@@ -656,6 +656,13 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         a.R = x_in; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b;
         a.r_save = save ? la.r1 : nullptr; a.st_save = save ? la.st1 : nullptr;
         if ((rc = linear(a, EPI_RES_LN, 4 * li + TC_W_OUT, (fuse_embed && li == 0) ? 2 : 0))) return rc;
+        if (use_tc && !save && d == 64 && tc_ffn_fused_enabled()) {
+            // ffn.0 -> relu -> ffn.2 -> relu -> +x1 -> LN2 in one tcgen05 kernel; the hidden activations stay on the SM
+            if ((rc = launch_ffn_tc(la.x1, la.x2, P, G, pk, tab.e[4 * li + TC_W_F1].pk_off, tab.e[4 * li + TC_W_F2].pk_off,
+                                    lo.f1_b, lo.f2_b, lo.ln2_w, lo.ln2_b, (int)Tg, st))) return rc;
+            x_in = la.x2;
+            continue;
+        }
         // ffn.0 + relu
         a.X = la.x1; a.Y = la.h; a.w_off = lo.f1_w; a.b_off = lo.f1_b; a.N = 4 * d; a.K = d;
         if ((rc = linear(a, EPI_BIAS_RELU, 4 * li + TC_W_F1))) return rc;

@@ -192,6 +192,9 @@ int dtqn_set_seq_fused(int32_t on);
 /* 1: the acting forward recomputes the token embedding inside the tcgen05 in_proj / out_proj kernels of layer 0
  * (continuous observations) instead of materialising it; 0 (default, measured faster): separate embed kernel. */
 int dtqn_set_tc_fuse_embed(int32_t on);
+/* 1 (default): on the tcgen05 path (d_model 64, inference) ffn.0 -> ReLU -> ffn.2 -> ReLU -> +residual -> LayerNorm run as
+ * ONE kernel with the hidden activations kept in TMEM / shared memory; 0: two Linear launches. */
+int dtqn_set_tc_fuse_ffn(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 
