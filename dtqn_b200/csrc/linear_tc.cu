@@ -716,7 +716,7 @@ linear_tc_pipe_kernel(TcArgs t) {
 //   warps 13-16 LayerNorm epilogue: acc2 -> +b2 -> ReLU -> +x1 -> LN -> staged, full-line stores
 // TMEM: acc1 = 256 columns (4 chunks), acc2 = 2 x 64 columns (double buffered across tiles).
 // =================================================================================================================================
-constexpr int FFN_THREADS = PIPE_PRODUCERS + 32 + 128 + 128;
+constexpr int FFN_THREADS = PIPE_PRODUCERS + 32 + 256 + 128;   // 8 producer + 1 MMA + 8 hidden-epilogue + 4 LayerNorm-epilogue warps
 
 struct FfnArgs {
     const float* X;            // x1 [G*Tg, 64]  (input and LayerNorm residual)
@@ -743,15 +743,14 @@ ffn_tc_kernel(FfnArgs t) {
     uint8_t* sW1 = base;
     uint8_t* sW2 = sW1 + W1_BYTES;                             // 2 stages
     uint8_t* sA1 = sW2 + 2 * W2C_BYTES;
-    uint8_t* sA2 = sA1 + A_STAGE_BYTES;
-    uint8_t* sStg = sA2 + A_STAGE_BYTES;                       // residual rows, then output rows (same region)
-    float* sB1 = reinterpret_cast<float*>(sStg + STG_BYTES);   // b1[256] | b2[64] | gamma[64] | beta[64]
+    uint8_t* sA2 = sA1 + A_STAGE_BYTES;                        // 2 stages: hidden chunk n -> stage n & 1
+    float* sB1 = reinterpret_cast<float*>(sA2 + 2 * A_STAGE_BYTES);   // b1[256] | b2[64] | gamma[64] | beta[64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + HID + 3 * D);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    enum { W1_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, ACC1_FULL = 3, ACC1_EMPTY = 4, A2_FULL = 5, A2_EMPTY = 6,
-           W2_FULL = 7 /*+s*/, W2_EMPTY = 9 /*+s*/, ACC2_FULL = 11 /*+as*/, ACC2_EMPTY = 13 /*+as*/ };
+    enum { W1_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, ACC1_FULL = 3, ACC1_EMPTY = 4, A2_FULL = 5 /*+s*/, A2_EMPTY = 7 /*+s*/,
+           W2_FULL = 9 /*+s*/, W2_EMPTY = 11 /*+s*/, ACC2_FULL = 13 /*+as*/, ACC2_EMPTY = 15 /*+as*/ };
 
     const float* p = t.P.p[g];
     for (int e = tid; e < HID; e += FFN_THREADS) sB1[e] = __ldg(p + t.b1_off + e);
@@ -763,9 +762,9 @@ ffn_tc_kernel(FfnArgs t) {
     if (tid == 0) {
         mbar_init(BAR(W1_FULL), 1);
         mbar_init(BAR(A1_FULL), PIPE_PRODUCERS); mbar_init(BAR(A1_EMPTY), 1);
-        mbar_init(BAR(ACC1_FULL), 1); mbar_init(BAR(ACC1_EMPTY), 128);
-        mbar_init(BAR(A2_FULL), 128); mbar_init(BAR(A2_EMPTY), 1);
+        mbar_init(BAR(ACC1_FULL), 1); mbar_init(BAR(ACC1_EMPTY), 256);
         for (int k = 0; k < 2; ++k) {
+            mbar_init(BAR(A2_FULL + k), 256); mbar_init(BAR(A2_EMPTY + k), 1);
             mbar_init(BAR(W2_FULL + k), 1); mbar_init(BAR(W2_EMPTY + k), 1);
             mbar_init(BAR(ACC2_FULL + k), 1); mbar_init(BAR(ACC2_EMPTY + k), 128);
         }
@@ -842,13 +841,11 @@ ffn_tc_kernel(FfnArgs t) {
             bool ok = mbar_wait(BAR(W1_FULL), 0);
             const uint32_t idesc = umma_idesc(TC_M, 64);
             const uint32_t sA1_u = smem_u32(sA1), sA2_u = smem_u32(sA2), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
-            for (int i = 0; i < my_tiles && ok; ++i) {
-                const int as = i & 1;
-                ok = mbar_wait(BAR(A1_FULL), (uint32_t)(i & 1));
-                if (ok && i >= 1) ok = mbar_wait(BAR(ACC1_EMPTY), (uint32_t)((i - 1) & 1));
-                if (!ok) break;
+            auto mma1 = [&](int i) -> bool {                   // hidden[128 x 256] of tile i = x1 W1^T, four N = 64 chunks
+                bool o = mbar_wait(BAR(A1_FULL), (uint32_t)(i & 1));
+                if (o && i >= 1) o = mbar_wait(BAR(ACC1_EMPTY), (uint32_t)((i - 1) & 1));
+                if (!o) return false;
                 tc_fence_after();
-                // MMA1: hidden[128 x 256] = x1[128 x 64] W1^T, as four N = 64 column chunks of the resident W1 image
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
 #pragma unroll
@@ -865,28 +862,36 @@ ffn_tc_kernel(FfnArgs t) {
                 }
                 umma_commit(BAR(A1_EMPTY));
                 umma_commit(BAR(ACC1_FULL));
+                return true;
+            };
+            if (ok && my_tiles > 0) ok = mma1(0);
+            for (int i = 0; i < my_tiles && ok; ++i) {
+                const int as = i & 1;
                 // MMA2: out[128 x 64] += relu(hidden chunk c)[128 x 64] W2[:, chunk c]^T
                 for (int c = 0; c < NCH && ok; ++c) {
                     const int n = i * NCH + c, s_ = n & 1, m = n >> 1;
                     ok = mbar_wait(BAR(W2_FULL + s_), (uint32_t)(m & 1));
-                    if (ok) ok = mbar_wait(BAR(A2_FULL), (uint32_t)(n & 1));
+                    if (ok) ok = mbar_wait(BAR(A2_FULL + s_), (uint32_t)(m & 1));
                     if (ok && c == 0 && i >= 2) ok = mbar_wait(BAR(ACC2_EMPTY + as), (uint32_t)(((i >> 1) - 1) & 1));
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t wb = sW2_u + (uint32_t)s_ * W2C_BYTES;
+                    const uint32_t ab = sA2_u + (uint32_t)s_ * A_STAGE_BYTES;
 #pragma unroll
                     for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
-                        const uint64_t a_hi = umma_desc(sA2_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
-                        const uint64_t a_lo = umma_desc(sA2_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t a_hi = umma_desc(ab + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                        const uint64_t a_lo = umma_desc(ab + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
                         const uint64_t b_hi = umma_desc(wb + k16 * 2 * (D * 16), D * 16, 128);
                         const uint64_t b_lo = umma_desc(wb + W2C_HALF + k16 * 2 * (D * 16), D * 16, 128);
                         umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_hi, b_hi, idesc, (c | k16) ? 1u : 0u);
                         umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_hi, b_lo, idesc, 1u);
                         umma_bf16(tm_acc2 + (uint32_t)(as * 64), a_lo, b_hi, idesc, 1u);
                     }
-                    umma_commit(BAR(A2_EMPTY));
+                    umma_commit(BAR(A2_EMPTY + s_));
                     umma_commit(BAR(W2_EMPTY + s_));
-                    if (n + 2 < n_total) {                     // refill this ring stage once its MMAs have retired
+                    // the next tile's MMA1 is issued as soon as its operands are ready so the hidden epilogue never starves
+                    if (c == NCH - 2 && i + 1 < my_tiles) ok = mma1(i + 1);
+                    if (ok && n + 2 < n_total) {               // refill this W2 ring stage once its MMAs have retired
                         ok = mbar_wait(BAR(W2_EMPTY + s_), (uint32_t)(m & 1));
                         if (ok) load_w2(n + 2);
                     }
@@ -894,103 +899,89 @@ ffn_tc_kernel(FfnArgs t) {
                 if (ok) umma_commit(BAR(ACC2_FULL + as));
             }
         }
-    } else if (warp < 13) {
-        // ------------------------------------------------ hidden epilogue ------------------------------------------------
-        const int q4 = warp & 3, row = q4 * 32 + lane;
+    } else if (warp < 17) {
+        // -------------------------------- hidden epilogue: 8 warps, two per TMEM lane quarter, 32 columns each --------------------------------
+        const int q4 = warp & 3, row = q4 * 32 + lane, chalf = (warp - 9) >> 2;
         for (int i = 0; i < my_tiles; ++i) {
             if (!mbar_wait(BAR(ACC1_FULL), (uint32_t)(i & 1))) break;
             tc_fence_after();
             bool ok = true;
             for (int c = 0; c < NCH && ok; ++c) {
-                const int n = i * NCH + c;
-                uint32_t tv[4][16];
-                const uint32_t trow = tm_acc1 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 64);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) tmem_ld16_issue(trow + cc * 16, tv[cc]);
+                const int n = i * NCH + c, s_ = n & 1, m = n >> 1;
+                uint32_t tv[2][16];
+                const uint32_t trow = tm_acc1 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 64 + chalf * 32);
+                tmem_ld16_issue(trow, tv[0]);
+                tmem_ld16_issue(trow + 16, tv[1]);
                 tmem_ld_wait();
-                if (n >= 1) ok = mbar_wait(BAR(A2_EMPTY), (uint32_t)((n - 1) & 1));   // MMA2 of the previous chunk done with A2
+                if (m >= 1) ok = mbar_wait(BAR(A2_EMPTY + s_), (uint32_t)((m - 1) & 1));   // MMA2 of chunk n-2 done with this stage
                 if (!ok) break;
+                uint8_t* dst = sA2 + s_ * A_STAGE_BYTES;
 #pragma unroll
-                for (int sub = 0; sub < 8; ++sub) {
+                for (int sb = 0; sb < 4; ++sb) {
+                    const int sub = chalf * 4 + sb;             // 8-column group within the 64-column chunk
                     float x[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        x[e] = fmaxf(__uint_as_float(tv[sub >> 1][(sub & 1) * 8 + e]) + sB1[c * 64 + sub * 8 + e], 0.f);
+                        x[e] = fmaxf(__uint_as_float(tv[sb >> 1][(sb & 1) * 8 + e]) + sB1[c * 64 + sub * 8 + e], 0.f);
                     uint4 hi, lo;
                     split8(x, hi, lo);
-                    *reinterpret_cast<uint4*>(sA2 + sub * A_CHUNK_STRIDE + row * 16) = hi;
-                    *reinterpret_cast<uint4*>(sA2 + A_HALF_BYTES + sub * A_CHUNK_STRIDE + row * 16) = lo;
+                    *reinterpret_cast<uint4*>(dst + sub * A_CHUNK_STRIDE + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(dst + A_HALF_BYTES + sub * A_CHUNK_STRIDE + row * 16) = lo;
                 }
                 fence_async_smem();
-                mbar_arrive(BAR(A2_FULL));
+                mbar_arrive(BAR(A2_FULL + s_));
             }
             tc_fence_before();
             mbar_arrive(BAR(ACC1_EMPTY));
             if (!ok) break;
         }
     } else {
-        // ------------------------------------------------ LayerNorm epilogue ------------------------------------------------
+        // -------------------------------- LayerNorm epilogue: 4 warps, thread = row --------------------------------
         const int q4 = warp & 3, row_in_tile = q4 * 32 + lane;
         const float* sB2 = sB1 + HID; const float* sG = sB2 + D; const float* sBe = sG + D;
-        uint8_t* stg_w = sStg + (q4 * 32) * STG_ROW_BYTES;
-        const int half = lane >> 4, c16 = lane & 15;
         for (int i = 0; i < my_tiles; ++i) {
             const int as = i & 1;
             const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TC_M;
-            const int rows_valid = min(32, t.Tg - (m0 + q4 * 32));
-            {   // residual rows of this warp -> staging (full-line loads, all in flight)
-                const float* src0 = t.X + (grow + m0 + q4 * 32) * (size_t)D;
-                float4 rv[16];
+            const int r = m0 + row_in_tile;
+            const bool row_ok = r < t.Tg;
+            const size_t ro = (grow + (row_ok ? r : 0)) * (size_t)D;
+            float u[D];
 #pragma unroll
-                for (int rr = 0; rr < 16; ++rr) {
-                    const int rw = 2 * rr + half;
-                    rv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rw < rows_valid) rv[rr] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)rw * D + c16 * 4));
-                }
-#pragma unroll
-                for (int rr = 0; rr < 16; ++rr)
-                    *reinterpret_cast<float4*>(stg_w + (2 * rr + half) * STG_ROW_BYTES + c16 * 16) = rv[rr];
-                __syncwarp();
+            for (int q = 0; q < D; q += 4) {                   // residual row (in flight while the MMAs run)
+                const float4 xr = __ldg(reinterpret_cast<const float4*>(t.X + ro + q));
+                u[q] = xr.x; u[q + 1] = xr.y; u[q + 2] = xr.z; u[q + 3] = xr.w;
             }
             if (!mbar_wait(BAR(ACC2_FULL + as), (uint32_t)((i >> 1) & 1))) break;
             tc_fence_after();
             const uint32_t trow = tm_acc2 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 64);
-            uint32_t tv[4][16];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) tmem_ld16_issue(trow + cc * 16, tv[cc]);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(BAR(ACC2_EMPTY + as));                 // accumulator copied to registers: MMA2 of tile i+2 may start
-            float u[D];
             float s = 0.f;
-            const uint8_t* myrow = stg_w + lane * STG_ROW_BYTES;
 #pragma unroll
-            for (int q = 0; q < D; q += 4) {
-                const float4 xr = *reinterpret_cast<const float4*>(myrow + q * 4);
-                const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t tv[16];
+                tmem_ld16_issue(trow + cc * 16, tv);
+                tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    u[q + e] = xv[e] + fmaxf(__uint_as_float(tv[(q + e) >> 4][(q + e) & 15]) + sB2[q + e], 0.f);
-                    s += u[q + e];
+                for (int e = 0; e < 16; ++e) {
+                    u[cc * 16 + e] += fmaxf(__uint_as_float(tv[e]) + sB2[cc * 16 + e], 0.f);
+                    s += u[cc * 16 + e];
                 }
             }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC2_EMPTY + as));                 // accumulator consumed: MMA2 of tile i+2 may start
             const float mean = s * (1.f / D);
             float vs = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) { const float dl = u[j] - mean; vs = fmaf(dl, dl, vs); }
             const float rstd = 1.0f / sqrtf(vs * (1.f / D) + 1e-5f);
-            __syncwarp();                                      // every lane has consumed its residual row
-            uint8_t* mystg = stg_w + lane * STG_ROW_BYTES;
+            if (row_ok) {
 #pragma unroll
-            for (int q = 0; q < D; q += 4) {
-                float o[4];
+                for (int q = 0; q < D; q += 4) {
+                    float o[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = (u[q + e] - mean) * rstd * sG[q + e] + sBe[q + e];
-                *reinterpret_cast<float4*>(mystg + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int e = 0; e < 4; ++e) o[e] = (u[q + e] - mean) * rstd * sG[q + e] + sBe[q + e];
+                    *reinterpret_cast<float4*>(t.Y + ro + q) = make_float4(o[0], o[1], o[2], o[3]);
+                }
             }
-            if (rows_valid > 0)
-                warp_store_rows(stg_w, t.Y + (grow + m0 + q4 * 32) * (size_t)D, (size_t)D, rows_valid, lane);
-            else { __syncwarp(); __syncwarp(); }
         }
     }
     tc_fence_before();
@@ -1055,7 +1046,7 @@ int launch_ffn_tc(const float* X, float* Y, const GroupPtrs& P, int G, const uin
     t.X = X; t.Y = Y; t.P = P; t.pk_w1 = pk_w1; t.pk_w2 = pk_w2; t.b1_off = b1_off; t.b2_off = b2_off;
     t.gamma_off = gamma_off; t.beta_off = beta_off; t.Tg = Tg;
     for (int g = 0; g < G; ++g) t.packed[g] = packed[g];
-    constexpr size_t smem = 1024 + 256 * TC_KC * 4 + 2 * 64 * TC_KC * 4 + 2 * A_STAGE_BYTES + STG_BYTES + (256 + 3 * 64) * 4 + 256;
+    constexpr size_t smem = 1024 + 256 * TC_KC * 4 + 2 * 64 * TC_KC * 4 + 3 * A_STAGE_BYTES + (256 + 3 * 64) * 4 + 256;
     static_assert(smem <= 227 * 1024, "fused FFN: shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
