@@ -746,11 +746,11 @@ ffn_tc_kernel(FfnArgs t) {
     uint8_t* sA2 = sA1 + A_STAGE_BYTES;                        // 2 stages: hidden chunk n -> stage n & 1
     float* sB1 = reinterpret_cast<float*>(sA2 + 2 * A_STAGE_BYTES);   // b1[256] | b2[64] | gamma[64] | beta[64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + HID + 3 * D);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 28);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    enum { W1_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, ACC1_FULL = 3, ACC1_EMPTY = 4, A2_FULL = 5 /*+s*/, A2_EMPTY = 7 /*+s*/,
-           W2_FULL = 9 /*+s*/, W2_EMPTY = 11 /*+s*/, ACC2_FULL = 13 /*+as*/, ACC2_EMPTY = 15 /*+as*/ };
+    enum { W1_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, A2_FULL = 3 /*+s*/, A2_EMPTY = 5 /*+s*/, W2_FULL = 7 /*+s*/, W2_EMPTY = 9 /*+s*/,
+           ACC2_FULL = 11 /*+as*/, ACC2_EMPTY = 13 /*+as*/, ACC1_FULL = 15 /*+c*/, ACC1_EMPTY = 19 /*+c*/ };
 
     const float* p = t.P.p[g];
     for (int e = tid; e < HID; e += FFN_THREADS) sB1[e] = __ldg(p + t.b1_off + e);
@@ -762,7 +762,7 @@ ffn_tc_kernel(FfnArgs t) {
     if (tid == 0) {
         mbar_init(BAR(W1_FULL), 1);
         mbar_init(BAR(A1_FULL), PIPE_PRODUCERS); mbar_init(BAR(A1_EMPTY), 1);
-        mbar_init(BAR(ACC1_FULL), 1); mbar_init(BAR(ACC1_EMPTY), 256);
+        for (int k = 0; k < 4; ++k) { mbar_init(BAR(ACC1_FULL + k), 1); mbar_init(BAR(ACC1_EMPTY + k), 256); }
         for (int k = 0; k < 2; ++k) {
             mbar_init(BAR(A2_FULL + k), 256); mbar_init(BAR(A2_EMPTY + k), 1);
             mbar_init(BAR(W2_FULL + k), 1); mbar_init(BAR(W2_EMPTY + k), 1);
@@ -841,35 +841,37 @@ ffn_tc_kernel(FfnArgs t) {
             bool ok = mbar_wait(BAR(W1_FULL), 0);
             const uint32_t idesc = umma_idesc(TC_M, 64);
             const uint32_t sA1_u = smem_u32(sA1), sA2_u = smem_u32(sA2), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
-            auto mma1 = [&](int i) -> bool {                   // hidden[128 x 256] of tile i = x1 W1^T, four N = 64 chunks
-                bool o = mbar_wait(BAR(A1_FULL), (uint32_t)(i & 1));
-                if (o && i >= 1) o = mbar_wait(BAR(ACC1_EMPTY), (uint32_t)((i - 1) & 1));
+            // MMA1 of one 64-column hidden chunk: acc1[c] of tile i = x1 W1[c]^T.  acc1[c] is free as soon as the hidden epilogue
+            // has copied chunk c of tile i-1 to registers, so MMA1 runs a whole tile ahead of the conversion work.
+            auto mma1_chunk = [&](int i, int c) -> bool {
+                bool o = true;
+                if (c == 0) o = mbar_wait(BAR(A1_FULL), (uint32_t)(i & 1));
+                if (o && i >= 1) o = mbar_wait(BAR(ACC1_EMPTY + c), (uint32_t)((i - 1) & 1));
                 if (!o) return false;
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-                    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
-                        const uint64_t a_hi = umma_desc(sA1_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
-                        const uint64_t a_lo = umma_desc(sA1_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
-                        const uint32_t boff = (uint32_t)(k16 * 2 * (HID * 16) + c * 64 * 16);
-                        const uint64_t b_hi = umma_desc(sW1_u + boff, HID * 16, 128);
-                        const uint64_t b_lo = umma_desc(sW1_u + W1_HALF + boff, HID * 16, 128);
-                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_hi, idesc, k16 ? 1u : 0u);
-                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_lo, idesc, 1u);
-                        umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_lo, b_hi, idesc, 1u);
-                    }
+                for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+                    const uint64_t a_hi = umma_desc(sA1_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                    const uint64_t a_lo = umma_desc(sA1_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+                    const uint32_t boff = (uint32_t)(k16 * 2 * (HID * 16) + c * 64 * 16);
+                    const uint64_t b_hi = umma_desc(sW1_u + boff, HID * 16, 128);
+                    const uint64_t b_lo = umma_desc(sW1_u + W1_HALF + boff, HID * 16, 128);
+                    umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_hi, idesc, k16 ? 1u : 0u);
+                    umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_hi, b_lo, idesc, 1u);
+                    umma_bf16(tm_acc1 + (uint32_t)(c * 64), a_lo, b_hi, idesc, 1u);
                 }
-                umma_commit(BAR(A1_EMPTY));
-                umma_commit(BAR(ACC1_FULL));
+                umma_commit(BAR(ACC1_FULL + c));
+                if (c == NCH - 1) umma_commit(BAR(A1_EMPTY));   // A1 stage free once all four chunks have read it
                 return true;
             };
-            if (ok && my_tiles > 0) ok = mma1(0);
+            for (int c = 0; c < NCH && ok && my_tiles > 0; ++c) ok = mma1_chunk(0, c);
             for (int i = 0; i < my_tiles && ok; ++i) {
                 const int as = i & 1;
-                // MMA2: out[128 x 64] += relu(hidden chunk c)[128 x 64] W2[:, chunk c]^T
                 for (int c = 0; c < NCH && ok; ++c) {
                     const int n = i * NCH + c, s_ = n & 1, m = n >> 1;
+                    if (i + 1 < my_tiles) ok = mma1_chunk(i + 1, c);               // next tile's hidden chunk c
+                    if (!ok) break;
+                    // MMA2: out[128 x 64] += relu(hidden chunk c)[128 x 64] W2[:, chunk c]^T
                     ok = mbar_wait(BAR(W2_FULL + s_), (uint32_t)(m & 1));
                     if (ok) ok = mbar_wait(BAR(A2_FULL + s_), (uint32_t)(m & 1));
                     if (ok && c == 0 && i >= 2) ok = mbar_wait(BAR(ACC2_EMPTY + as), (uint32_t)(((i >> 1) - 1) & 1));
@@ -889,9 +891,7 @@ ffn_tc_kernel(FfnArgs t) {
                     }
                     umma_commit(BAR(A2_EMPTY + s_));
                     umma_commit(BAR(W2_EMPTY + s_));
-                    // the next tile's MMA1 is issued as soon as its operands are ready so the hidden epilogue never starves
-                    if (c == NCH - 2 && i + 1 < my_tiles) ok = mma1(i + 1);
-                    if (ok && n + 2 < n_total) {               // refill this W2 ring stage once its MMAs have retired
+                    if (n + 2 < n_total) {                     // refill this W2 ring stage once its MMAs have retired
                         ok = mbar_wait(BAR(W2_EMPTY + s_), (uint32_t)(m & 1));
                         if (ok) load_w2(n + 2);
                     }
@@ -903,16 +903,19 @@ ffn_tc_kernel(FfnArgs t) {
         // -------------------------------- hidden epilogue: 8 warps, two per TMEM lane quarter, 32 columns each --------------------------------
         const int q4 = warp & 3, row = q4 * 32 + lane, chalf = (warp - 9) >> 2;
         for (int i = 0; i < my_tiles; ++i) {
-            if (!mbar_wait(BAR(ACC1_FULL), (uint32_t)(i & 1))) break;
-            tc_fence_after();
             bool ok = true;
             for (int c = 0; c < NCH && ok; ++c) {
                 const int n = i * NCH + c, s_ = n & 1, m = n >> 1;
+                ok = mbar_wait(BAR(ACC1_FULL + c), (uint32_t)(i & 1));
+                if (!ok) break;
+                tc_fence_after();
                 uint32_t tv[2][16];
                 const uint32_t trow = tm_acc1 + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 64 + chalf * 32);
                 tmem_ld16_issue(trow, tv[0]);
                 tmem_ld16_issue(trow + 16, tv[1]);
                 tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(BAR(ACC1_EMPTY + c));              // chunk copied to registers: MMA1 of the next tile may overwrite it
                 if (m >= 1) ok = mbar_wait(BAR(A2_EMPTY + s_), (uint32_t)((m - 1) & 1));   // MMA2 of chunk n-2 done with this stage
                 if (!ok) break;
                 uint8_t* dst = sA2 + s_ * A_STAGE_BYTES;
@@ -931,8 +934,6 @@ ffn_tc_kernel(FfnArgs t) {
                 fence_async_smem();
                 mbar_arrive(BAR(A2_FULL + s_));
             }
-            tc_fence_before();
-            mbar_arrive(BAR(ACC1_EMPTY));
             if (!ok) break;
         }
     } else {
