@@ -247,3 +247,42 @@ def test_acting_forward_embed_fusion_matches_unfused(golden_dir):
     torch.cuda.synchronize()
     assert torch.isfinite(q_fused).all()
     assert (q_fused - q_plain).abs().max().item() <= 1e-5 * max(1.0, q_plain.abs().max().item())
+
+
+@pytest.mark.parametrize("pos,history", [("sin", 50), ("none", 50), ("learned", 10)])
+def test_train_step_ablation_flags_vs_oracle(pos, history):
+    """--pos sin | none (non-trainable position table, position_encodings.py:22-51) and --history < context
+    (agents/dtqn.py:240-241: loss over the last `history` positions only) against the CPU oracle."""
+    from dtqn_b200.agents import DtqnAgent
+    from dtqn_b200.networks import DTQN
+    from oracle import network as onet, agent as oagent
+    g = torch.Generator().manual_seed(77)
+    O, A, d, ctx, B = 3, 3, 64, 50, 6
+    sd = onet.init_state_dict(O, A, 8, d, 8, 2, ctx, pos=pos, generator=g)
+    for k, v in sd.items():
+        if k.endswith("attn_mask") or "position_encoding" in k:
+            continue
+        v.mul_(3.0) if v.dim() > 1 else v.add_(torch.empty_like(v).normal_(0, 0.05, generator=g))
+
+    def mk():
+        net = DTQN(O, A, 8, 0, d, 8, 2, ctx, pos=pos, device="cuda")
+        net.load_state_dict(sd)
+        return net
+    agent = DtqnAgent(mk, 4000, "cuda", O, 200, -5, A, False, batch_size=B, context_len=ctx, history=history)
+    assert not agent.policy_network.position_embedding.position_encoding.requires_grad or pos == "learned"
+    win = torch.empty(B, ctx + 1, O).uniform_(-1.1, 1.1, generator=g)
+    act = torch.randint(0, A, (B, ctx + 1), generator=g).to(torch.uint8)
+    rew = torch.randint(-1, 2, (B, ctx), generator=g).float()
+    done = (torch.rand(B, ctx, generator=g) < 0.1).to(torch.uint8)
+    agent.train_on_windows(win.cuda(), act.cuda(), rew.cuda(), done.cuda())
+    tr = oagent.TrainerOracle(sd, 8, pos=pos, history=history)
+    batch = (win[:, :-1], act[:, :-1, None].long(), rew[..., None], win[:, 1:], act[:, 1:, None].long(), done[..., None].bool())
+    stats, grads = tr.train_on_batch(batch)
+    st = agent.stats.cpu().numpy()
+    assert abs(st[0] - stats["loss"]) <= 1e-4 * max(1, abs(stats["loss"]))
+    assert abs(st[7] - stats["grad_norm"]) <= 2e-4 * max(1, stats["grad_norm"])
+    new = agent.policy_network.state_dict()
+    for k in tr.keys:
+        assert float((new[k].cpu() - tr.policy[k]).abs().max()) < 3e-5, k
+    if pos != "learned":      # the fixed table is untouched by the optimiser
+        assert torch.equal(new["position_embedding.position_encoding"].cpu(), sd["position_embedding.position_encoding"])

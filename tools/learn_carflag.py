@@ -1,0 +1,37 @@
+"""End-to-end learning check: train DTQN on 4096 lockstep CarFlag envs with the reference hyper-parameters (batch 32,
+lr 3e-4, tuf 10 000, gamma 0.99, ctx 50, eps geometric 1.0 -> 0.1 over num_steps/10) and log the greedy evaluation success
+rate (run.evaluate semantics) over training.  Usage: python tools/learn_carflag.py [iterations] [eval_every]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dtqn_b200.runner import BatchedTrainer
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+every = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
+tr = BatchedTrainer("DiscreteCarFlag-v0", n_envs=4096, seed=1, device="cuda", inner_embed=64, context=50, batch=32,
+                    num_steps=iters)
+tr.prepopulate(260)
+tr.enable_graphs()
+log = []
+sr, ret, length = tr.evaluate(1)
+log.append(dict(iteration=0, env_steps=0, success_rate=sr, mean_return=ret, episode_length=length))
+print(json.dumps(log[-1]), flush=True)
+t0 = time.time()
+for it in range(1, iters + 1):
+    tr.train_iteration()
+    if it % every == 0:
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        sr, ret, length = tr.evaluate(1)
+        a = tr.agent
+        log.append(dict(iteration=it, env_steps=it * 4096, success_rate=sr, mean_return=ret, episode_length=length,
+                        td_error=a.td_errors.mean(), q_mean=a.qvalue_mean.mean(), grad_norm=a.grad_norms.mean(),
+                        epsilon=tr.eps.val, train_wall_s=wall))
+        print(json.dumps(log[-1]), flush=True)
+        t0 = time.time() - wall          # exclude evaluation time from the training clock
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(log, open("gpurun_out/learn_carflag.json", "w"), indent=1)
