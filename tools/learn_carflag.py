@@ -14,8 +14,9 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 every = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 trunc = bool(int(sys.argv[4])) if len(sys.argv) > 4 else True       # 1 = the reference's integer acting context (A-Q2)
+tuf = int(sys.argv[5]) if len(sys.argv) > 5 else 10_000             # --tuf: one Bellman backup per target sync
 tr = BatchedTrainer("DiscreteCarFlag-v0", n_envs=4096, seed=1, device="cuda", inner_embed=64, context=50, batch=batch,
-                    num_steps=iters, trunc_context_obs=trunc)
+                    num_steps=iters, trunc_context_obs=trunc, tuf=tuf)
 tr.prepopulate(260)
 tr.enable_graphs()
 log = []
@@ -36,4 +37,4 @@ for it in range(1, iters + 1):
         print(json.dumps(log[-1]), flush=True)
         t0 = time.time() - wall          # exclude evaluation time from the training clock
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(dict(batch=batch, trunc_context_obs=trunc, log=log), open(f"gpurun_out/learn_carflag_b{batch}_t{int(trunc)}.json", "w"), indent=1)
+json.dump(dict(batch=batch, trunc_context_obs=trunc, tuf=tuf, log=log), open(f"gpurun_out/learn_carflag_b{batch}_t{int(trunc)}_tuf{tuf}.json", "w"), indent=1)
