@@ -209,6 +209,8 @@ class DTQN(nn.Module):
         """obss [B, L, O] (float, or integer ids for discrete envs) -> Q [B, L, A] (dtqn.py:158-218)."""
         assert obss.dim() == 3, "obss is batch x seq_len x obs_dim"
         B, L, O = obss.shape
+        if B == 0 or L == 0:
+            return torch.empty((B, L, self.num_actions), dtype=torch.float32, device=self.flat.device)
         assert L <= self.history_len, "Cannot forward, history is longer than expected."           # dtqn.py:171-173
         assert O == self.obs_dim, f"Obs dim is incorrect. Expected {self.obs_dim} got {O}"          # dtqn.py:177-179
         x = obss.to(device=self.flat.device, dtype=torch.float32).contiguous()

@@ -36,8 +36,9 @@ def gather(eps, starts):
 
 pe = valid[:16]; ps = np.zeros(16, dtype=np.int64)
 probe = torch.from_numpy(obss[pe[:, None], np.arange(ctx)[None, :]])
-# terminal transitions of short episodes (window start 0 covers them)
-short = valid[lens[valid] <= ctx][:256]
+# windows that end at the terminal transition of episodes that reached heaven / hell
+term = valid[rews[valid, lens[valid] - 1, 0] != 0][:256]
+tstart = np.maximum(0, lens[term] - ctx)
 t0 = time.time()
 for k in range(1, K + 1):
     eps = rng.choice(valid, size=B)
@@ -50,13 +51,14 @@ for k in range(1, K + 1):
             qo = onet.forward(tr.policy, probe, 8).numpy()
         qg = agent.policy_network(probe).cpu().numpy()
         # terminal fit: Q(s_{T-1}, a_{T-1}) vs reward, on short episodes
-        xs = torch.from_numpy(obss[short[:, None], np.arange(ctx)[None, :]])
+        xs = torch.from_numpy(obss[term[:, None], tstart[:, None] + np.arange(ctx)[None, :]])
         with torch.no_grad():
             qso = onet.forward(tr.policy, xs, 8).numpy()
         qsg = agent.policy_network(xs).cpu().numpy()
-        T = lens[short] - 1
-        a_T = acts[short, T, 0]; r_T = rews[short, T, 0]
-        fit_o = np.abs(qso[np.arange(len(short)), T, a_T] - r_T).mean(); fit_g = np.abs(qsg[np.arange(len(short)), T, a_T] - r_T).mean()
+        T = lens[term] - 1
+        Tw = T - tstart
+        a_T = acts[term, T, 0]; r_T = rews[term, T, 0]
+        fit_o = np.abs(qso[np.arange(len(term)), Tw, a_T] - r_T).mean(); fit_g = np.abs(qsg[np.arange(len(term)), Tw, a_T] - r_T).mean()
         print(json.dumps(dict(step=k, loss_gpu=float(g_stats[0]), loss_oracle=stats["loss"], gnorm_gpu=float(g_stats[7]), gnorm_oracle=stats["grad_norm"],
                               probe_q_maxdiff=float(np.abs(qo - qg).max()), probe_q_absmax=float(np.abs(qo).max()),
                               terminal_fit_err_gpu=float(fit_g), terminal_fit_err_oracle=float(fit_o), wall_s=round(time.time() - t0, 1))), flush=True)
