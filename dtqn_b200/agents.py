@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from dtqn_b200 import _lib
+from dtqn_b200 import _lib, checkpoint
 from dtqn_b200.buffers import ReplayBuffer
 from dtqn_b200.envs import ContextWindow
 from dtqn_b200.networks import DTQN, NetCfg, ObsSrc, forward_groups
@@ -130,6 +130,22 @@ class DtqnAgent:
         """Hard update (dqn.py:208-210): one flat device-to-device copy."""
         self.target_network.flat.copy_(self.policy_network.flat)
         self.target_network.packed_stale = True
+
+    # ---- checkpoint / resume (dqn.py:212-327; file format in dtqn_b200/checkpoint.py) ----------------------------------------
+    def save_mini_checkpoint(self, checkpoint_dir: str, wandb_id: Optional[str]) -> None:
+        checkpoint.save_mini_checkpoint(self, checkpoint_dir, wandb_id)
+
+    @staticmethod
+    def load_mini_checkpoint(checkpoint_dir: str) -> dict:
+        return checkpoint.load_mini_checkpoint(checkpoint_dir)
+
+    def save_checkpoint(self, checkpoint_dir: str, wandb_id: Optional[str], episode_successes, episode_rewards,
+                        episode_lengths, eps) -> None:
+        checkpoint.save_agent(self, checkpoint_dir, wandb_id, episode_successes, episode_rewards, episode_lengths, eps)
+
+    def load_checkpoint(self, checkpoint_dir: str):
+        """-> (wandb_id, episode_successes, episode_rewards, episode_lengths, epsilon) like dqn.py:281-327."""
+        return checkpoint.load_agent(self, checkpoint_dir)[:5]
 
     def check_finite(self) -> None:
         if int(self.flags.item()) != 0:

@@ -5,8 +5,11 @@
 
 One "timestep" of the reference loop (run.py:290) is one lockstep iteration here: every env takes one step and the agent
 takes one gradient step, so ``--num-steps`` iterations collect ``num-steps x n-envs x world`` transitions.  New flag (no
-reference analogue): ``--n-envs`` lockstep environments per GPU.  Logging / wandb / rendering / checkpoint flags are
-accepted for command-line compatibility; losses and evaluation results are printed (rank 0) every ``--eval-frequency``.
+reference analogue): ``--n-envs`` lockstep environments per GPU.  Logging / wandb / rendering flags are accepted for
+command-line compatibility; losses and evaluation results are printed (rank 0) every ``--eval-frequency``.
+Checkpoint / resume follows run.py:452-499,337-352,526-529: the same ``policies/<project>/<env>/model=..._seed=N`` path
+prefix, ``_mini_checkpoint.pt`` / ``_checkpoint.pt`` / ``buffer_*.sav`` files (one set per rank, suffix ``_rank<r>`` when
+world > 1), written when ``--time-limit`` expires and read back on the next launch.
 """
 import argparse
 import os
@@ -81,11 +84,33 @@ def run_experiment(args):
     if rank == 0:
         n = sum(p.numel() for p in tr.agent.policy_network.parameters())
         print(f"Creating {args.model} with {n} parameters")                      # run.py:447-450
-    # prepopulate 50 000 transitions (run.py:495) with the random policy, and at least until a batch can be sampled
-    steps = max(1, 50_000 // args.n_envs)
-    tr.prepopulate(steps)
-    while not tr.agent.replay_buffer.can_sample(args.batch):
-        tr.prepopulate(16)
+    policy_dir = os.path.join(os.getcwd(), "policies", args.project_name, *args.envs)          # run.py:452-460
+    os.makedirs(policy_dir, exist_ok=True)
+    policy_path = os.path.join(
+        policy_dir,
+        f"model={args.model}_envs={','.join(args.envs)}_obs_embed={args.obs_embed}_a_embed={args.a_embed}_in_embed={args.in_embed}"
+        f"_context={args.context}_heads={args.heads}_layers={args.layers}_batch={args.batch}_gate={args.gate}"
+        f"_identity={args.identity}_history={args.history}_pos={args.pos}_bag={args.bag_size}_seed={args.seed}")
+    ckpt = policy_path + (f"_rank{rank}" if world > 1 else "")
+    from dtqn_b200.checkpoint import RunningAverage
+    if os.path.exists(ckpt + "_mini_checkpoint.pt"):                                             # run.py:469-490
+        done_steps = tr.agent.load_mini_checkpoint(ckpt)["step"]
+        print(f"Found a mini checkpoint that completed {done_steps} training steps.")
+        if done_steps >= args.num_steps:
+            print("Removing checkpoint and exiting...")
+            if os.path.exists(ckpt + "_checkpoint.pt"):
+                os.remove(ckpt + "_checkpoint.pt")
+            if world > 1:
+                dist.destroy_process_group()
+            return tr
+        _, mean_success_rate, mean_reward, mean_episode_length = tr.load_checkpoint(ckpt)
+    else:
+        # prepopulate 50 000 transitions (run.py:495) with the random policy, and at least until a batch can be sampled
+        steps = max(1, 50_000 // args.n_envs)
+        tr.prepopulate(steps)
+        while not tr.agent.replay_buffer.can_sample(args.batch):
+            tr.prepopulate(16)
+        mean_success_rate, mean_reward, mean_episode_length = RunningAverage(10), RunningAverage(10), RunningAverage(10)
     if not args.no_graph:
         tr.enable_graphs()
     start = time.time()
@@ -93,17 +118,28 @@ def run_experiment(args):
         tr.train_iteration()
         if timestep % args.eval_frequency == 0:
             sr, ret, length = tr.evaluate(max(1, args.eval_episodes // 10))
+            mean_success_rate.add(sr); mean_reward.add(ret); mean_episode_length.add(length)     # run.py:316-318
             if rank == 0:
                 a = tr.agent
                 print(f"[{timestep}] env-steps {timestep * args.n_envs * world}  TD {a.td_errors.mean():.5f}  "
                       f"grad-norm {a.grad_norms.mean():.4f}  Q {a.qvalue_mean.mean():.4f}  "
                       f"{args.envs[0]}/SuccessRate {sr:.3f}  Return {ret:.3f}  EpisodeLength {length:.1f}  "
                       f"hours {(time.time() - start) / 3600:.3f}", flush=True)
-        if args.save_policy and timestep % 50_000 == 0 and rank == 0:
-            os.makedirs("policies", exist_ok=True)
-            torch.save(tr.agent.policy_network.state_dict(), os.path.join("policies", f"{args.project_name}_{args.envs[0]}.pt"))
-        if args.time_limit and (time.time() - start) / 3600 >= args.time_limit:
+        if args.save_policy and timestep % 50_000 == 0 and rank == 0:                           # run.py:337-338
+            torch.save(tr.agent.policy_network.state_dict(), policy_path)
+        stop = False
+        if args.time_limit and timestep % 64 == 0:                                              # run.py:340-353
+            stop = (time.time() - start) / 3600 >= args.time_limit
+            if world > 1:                        # every rank must take the same branch (the update holds a collective)
+                flag = torch.tensor([int(stop)], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                stop = bool(flag.item())
+        if stop:
+            print(f"Reached time limit. Saving checkpoint with {tr.agent.num_train_steps} steps completed.")
+            tr.save_checkpoint(ckpt, None, mean_success_rate, mean_reward, mean_episode_length)
             break
+    else:
+        tr.agent.save_mini_checkpoint(ckpt, None)                                               # run.py:526-529
     if world > 1:
         dist.destroy_process_group()
     return tr

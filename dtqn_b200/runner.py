@@ -6,7 +6,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from dtqn_b200 import _lib
+from dtqn_b200 import _lib, checkpoint
 from dtqn_b200.envs import BatchedEnv
 from dtqn_b200.parallel import broadcast_parameters, rank_world, shard_seed
 from dtqn_b200.utils import LinearAnneal, get_agent
@@ -124,15 +124,28 @@ class BatchedTrainer:
         self.eps.anneal()
         self.iterations += 1
 
+    def save_checkpoint(self, checkpoint_dir: str, wandb_id: Optional[str] = None, episode_successes=None,
+                        episode_rewards=None, episode_lengths=None) -> None:
+        """agent.save_checkpoint (dqn.py:222-279) + env streams, contexts and loop counters; one set of files per rank
+        (pass a per-rank prefix under torchrun)."""
+        checkpoint.save_trainer(self, checkpoint_dir, wandb_id, episode_successes, episode_rewards, episode_lengths)
+
+    def load_checkpoint(self, checkpoint_dir: str):
+        """-> (wandb_id, episode_successes, episode_rewards, episode_lengths); the loop continues bit-exactly."""
+        return checkpoint.load_trainer(self, checkpoint_dir)
+
+    def make_eval_env(self) -> BatchedEnv:
+        if self.eval_env is None:
+            self.eval_env = BatchedEnv(self.env.env_id, self.n_envs, seeds=self.env.seeds, device=self.device)
+            self.eval_env.attach(None, self.agent.eval_context)
+        return self.eval_env
+
     @torch.no_grad()
     def evaluate(self, eval_episodes_per_env: int = 1, max_steps: Optional[int] = None):
         """run.evaluate (run.py:187-243): greedy policy on a separate set of envs seeded like the train envs
         (utils/random.py:26-29), no replay writes.  Returns (success_rate, mean_return, mean_episode_length)."""
         agent = self.agent
-        if self.eval_env is None:
-            self.eval_env = BatchedEnv(self.env.env_id, self.n_envs, seeds=self.env.seeds, device=self.device)
-            self.eval_env.attach(None, agent.eval_context)
-        ev = self.eval_env
+        ev = self.make_eval_env()
         agent.eval_on()
         ev.reset_all()
         target = eval_episodes_per_env * self.n_envs
