@@ -368,7 +368,10 @@ def main():
                                    "(eps-greedy through the DTQN), 1 grad step per lockstep env step",
                        "envs_per_gpu": N, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (acting-forward activations, ~600 MB) exceeds the 126 MB L2; no flush",
-                       "cuda_graphs": bool(use_graph)},
+                       "cuda_graphs": bool(use_graph),
+                       "grad_collective": {"none": "none (1 GPU)", "nccl": "NCCL allreduce + clip/Adam kernels (outside the graph)",
+                                           "p2p-fused": "own kernel: flag barrier + NVLink peer reads + norm, then clip/Adam "
+                                                        "(inside the CUDA graph, no NCCL call)"}[tr.allreduce]},
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
                                                 "host obs/reward/done -> agent.train -> host loss"},

@@ -32,6 +32,10 @@ _l.dtqn_clip_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.
                               C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int32, C.c_void_p]
 _l.dtqn_clip_adam.restype = C.c_int
+_l.dtqn_allreduce_clip_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+_l.dtqn_allreduce_clip_adam.restype = C.c_int
 
 STAT_NAMES = ("td_errors", "qvalue_max", "qvalue_mean", "qvalue_min", "target_max", "target_mean", "target_min", "grad_norms")
 RING = 100   # RunningAverage(100), dtqn/agents/dqn.py:82-89
@@ -112,6 +116,15 @@ class DtqnAgent:
         self._q_last = torch.zeros((self.n_envs, self.num_actions), dtype=torch.float32, device=self.device)
         self._host_ctx = None          # single-env host-call API state
         self.strict_finite = False
+        self.exchange = None           # parallel.PeerExchange when the gradient exchange runs over NVLink peer memory
+
+    def use_peer_exchange(self, exchange) -> None:
+        """Route the gradient collective through ``exchange`` (parallel.PeerExchange): the backward writes the local
+        gradient straight into the IPC-exported buffer and the update becomes dtqn_allreduce_clip_adam (2 kernels,
+        no NCCL call, graph-capturable).  Must be called before a CUDA graph is captured."""
+        assert exchange.n == self.policy_network.n_flat
+        self.exchange = exchange
+        self.grads = exchange.grads
 
     # ---- mode / context (dqn.py:102-115) -------------------------------------------------------------------------------
     @property
@@ -148,6 +161,8 @@ class DtqnAgent:
         return checkpoint.load_agent(self, checkpoint_dir)[:5]
 
     def check_finite(self) -> None:
+        if self.exchange is not None and self.exchange.error():
+            raise RuntimeError("gradient exchange timed out waiting for a peer rank (dtqn_p2p_error)")
         if int(self.flags.item()) != 0:
             raise RuntimeError("The total norm for gradients is non-finite, so it cannot be clipped.")  # agents/dtqn.py:257-261
 
@@ -191,6 +206,17 @@ class DtqnAgent:
         """Gradient allreduce (the one collective, only when world > 1) -> /world -> global-norm clip -> Adam, identical
         on every rank."""
         net, st = self.policy_network, _lib.stream_ptr()
+        ex = self.exchange
+        if ex is not None:                                   # fused: barrier + NVLink reads + norm, then clip + Adam
+            _lib.check(_l.dtqn_allreduce_clip_adam(net.flat.data_ptr(), ex.bases, ex.rank, ex.world, net.n_flat,
+                                                   ex.reduced.data_ptr(), self.exp_avg.data_ptr(),
+                                                   self.exp_avg_sq.data_ptr(), self.grad_norm_clip, self.learning_rate,
+                                                   self.betas[0], self.betas[1], self.adam_eps, self.opt_step.data_ptr(),
+                                                   self.opt_scratch.data_ptr(), self.stats.data_ptr(),
+                                                   self.flags.data_ptr(), self.stats_ring.data_ptr(), RING, st),
+                       "dtqn_allreduce_clip_adam")
+            net.repack()
+            return
         scale = allreduce_gradients(self.grads)              # sum of per-rank mean-MSE gradients; scale = 1/world
         _lib.check(_l.dtqn_clip_adam(net.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), net.n_flat, scale, self.grad_norm_clip,

@@ -73,6 +73,20 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 }  // namespace
 
+// second half of the update on its own (the P2P gradient exchange in p2p.cu produces `partial` itself)
+int launch_clip_adam_only(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float grad_scale,
+                          float max_norm, float lr, float beta1, float beta2, float eps, const long long* step,
+                          const float* partial, int n_partial, float* stats, int* flags, float* ring, int ring_len,
+                          cudaStream_t st) {
+    int blocks = dtqn_cdiv(n, OPT_THREADS * 4);
+    if (blocks > OPT_MAX_BLOCKS) blocks = OPT_MAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    clip_adam_kernel<<<blocks, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1,
+                                                    beta2, eps, step, partial, n_partial, stats, flags, ring, ring_len);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
                               float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_counter,
                               float* scratch, float* stats_out, int32_t* flags_out, float* stats_ring, int32_t ring_len,

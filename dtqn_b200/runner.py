@@ -8,7 +8,7 @@ import torch.distributed as dist
 
 from dtqn_b200 import _lib, checkpoint
 from dtqn_b200.envs import BatchedEnv
-from dtqn_b200.parallel import broadcast_parameters, rank_world, shard_seed
+from dtqn_b200.parallel import broadcast_parameters, peer_exchange_wanted, rank_world, shard_seed, try_peer_exchange
 from dtqn_b200.utils import LinearAnneal, get_agent
 
 
@@ -35,6 +35,18 @@ class BatchedTrainer:
             broadcast_parameters(self.agent.policy_network.flat, src=0)
             self.agent.policy_network.packed_stale = True
             self.agent.target_update()
+        # the one collective of the update: fused NVLink peer-memory exchange when the node allows it, else NCCL
+        self.allreduce, self.allreduce_note = ("none" if world == 1 else "nccl"), ""
+        if world > 1 and peer_exchange_wanted(world):
+            ex, why = try_peer_exchange(self.agent.policy_network.n_flat, self.device)
+            if ex is not None:
+                self.agent.use_peer_exchange(ex)
+                self.allreduce = "p2p-fused"
+            else:
+                self.allreduce_note = why
+                if rank == 0:
+                    print(f"[dtqn_b200] peer-memory gradient exchange unavailable ({why}); using the NCCL allreduce", flush=True)
+        self._update_in_graph = world == 1 or self.allreduce == "p2p-fused"
         self.env.attach(self.agent.replay_buffer, self.agent.train_context)
         self.eps = LinearAnneal(1.0, 0.1, max(1, num_steps // 10))     # run.py:420
         self.env.reset_all()                                  # run.py:287-288
@@ -57,7 +69,7 @@ class BatchedTrainer:
         eps, starts = rb.draw_indices(agent.batch_size)
         rb.gather_windows(eps, starts, out=agent._win)
         agent.forward_backward(*agent._win[:4])
-        if self.world == 1:
+        if self._update_in_graph:
             agent.reduce_and_step()
 
     def enable_graphs(self) -> None:
@@ -77,7 +89,9 @@ class BatchedTrainer:
         with torch.cuda.graph(g):
             self._device_iteration()
         self._graph = g
-        self.agent.finish_step() if self.world == 1 else (self.agent.reduce_and_step(), self.agent.finish_step())
+        if not self._update_in_graph:
+            self.agent.reduce_and_step()
+        self.agent.finish_step()
         self.eps.anneal()
         self.iterations += 1
 
@@ -115,7 +129,7 @@ class BatchedTrainer:
         if self._graph is not None:
             self._eps_pinned[0] = float(self.eps.val)
             self._graph.replay()
-            if self.world > 1:
+            if not self._update_in_graph:
                 self.agent.reduce_and_step()
             self.agent.finish_step()
         else:

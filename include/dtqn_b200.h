@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DTQN_ABI_VERSION 2
+#define DTQN_ABI_VERSION 3
 
 #define DTQN_E_ARG      (-1)  /* null pointer / out-of-range size */
 #define DTQN_E_UNSUPPORTED (-2)
@@ -224,6 +224,30 @@ int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
                    float* scratch /* >= 1024 floats */, float* stats_out, int32_t* flags_out,
                    float* stats_ring /* nullable [ring_len, 8]: row (step-1) % ring_len <- stats_out[0..8) */,
                    int32_t ring_len, void* stream);
+
+/* ---- multi-GPU: gradient exchange fused with the optimiser over NVLink peer memory -----------------------------------
+ * Replaces `allreduce(grads)` + dtqn_clip_adam when every rank of the node can map its peers' memory (SURVEY.md section
+ * 8e: one collective per update, after loss.backward() and before clip_grad_norm_, dtqn/agents/dtqn.py:256-261).
+ * Each rank allocates one exchange buffer (dtqn_p2p_alloc: header + n gradient floats, cudaMalloc'ed and IPC-exported),
+ * lets its backward write the local gradient into `*grads_out`, exchanges the 64-byte handles out of band (any host
+ * channel) and maps the peers with dtqn_p2p_open.  dtqn_allreduce_clip_adam then launches two kernels: (1) per-CTA
+ * flag barrier across ranks -> sum of all ranks' gradients read through NVLink in rank order (bit-identical on every
+ * rank) -> squared norm of the mean gradient -> end barrier; (2) the same clip + Adam kernel as dtqn_clip_adam with
+ * grad_scale = 1 / world.  No host synchronisation, graph-capturable (the barrier epoch lives in device memory).
+ * `bases[r]` = rank r's buffer as mapped in THIS process (own base at [rank]); n must be a multiple of 4.
+ * A peer that never arrives makes the bounded waits expire (~2 s) and sets an error flag: dtqn_p2p_error(base) != 0. */
+#define DTQN_P2P_MAX_RANKS 8
+#define DTQN_P2P_HANDLE_BYTES 64
+int dtqn_p2p_alloc(int64_t n_floats, void** base_out, float** grads_out, uint8_t* handle_out /* [64] */);
+int dtqn_p2p_open(const uint8_t* handle /* [64] */, void** peer_base_out);
+int dtqn_p2p_close(void* peer_base);
+int dtqn_p2p_free(void* base);
+int dtqn_p2p_error(const void* base);
+int dtqn_allreduce_clip_adam(float* params, void* const* bases, int32_t rank, int32_t world, int64_t n,
+                             float* grads_reduced /* [n] local output: sum over ranks */, float* exp_avg,
+                             float* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps,
+                             int64_t* step_counter, float* scratch, float* stats_out, int32_t* flags_out,
+                             float* stats_ring, int32_t ring_len, void* stream);
 
 
 /* ---- measurement hooks (bench.py roofline leg; no reference analogue) --------------------------------------------
