@@ -43,7 +43,8 @@ def main():
     torch.cuda.synchronize()
     tr.agent.check_finite()
     assert same_on_all_ranks(tr.agent.policy_network.flat), "replicas diverged"
-    assert same_on_all_ranks(tr.agent.exp_avg) and int(tr.agent.opt_step.item()) == tr.agent.num_train_steps == 25
+    assert same_on_all_ranks(tr.agent.exp_avg)
+    assert tr.agent.num_train_steps == 24 and int(tr.agent.opt_step.item()) == 25      # + the bare update of part 1
     rs = tr.env.rng_state()
     other = [None] * world
     dist.all_gather_object(other, rs[:4].tolist())
