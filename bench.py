@@ -327,7 +327,7 @@ def main():
                 graph_or_fn()
             b.record(); torch.cuda.synchronize()
             return a.elapsed_time(b) / n
-        tr._eps_pinned[0] = float(tr.eps.val)
+        tr._sync_epsilon_to_device()
         g_act, g_train = tr.capture(tr.act_only), tr.capture(tr.train_only)
         g_env = tr.capture(lambda: tr.env.step(mode=_lib.ACT_RANDOM))
         for g in (g_act, g_train, g_env):

@@ -330,9 +330,24 @@ int check_env(const dtqn_env* e, const dtqn_replay* rb, const dtqn_context* cx) 
     return 0;
 }
 
+// LinearAnneal.anneal (utils/epsilon_anneal.py:33-34) kept on the device so a replayed CUDA graph needs no per-step host
+// write: emit the current value for this step, then val <- max(min, val - (val - min) / duration), in double like the host.
+__global__ void eps_anneal_kernel(double* state, float* eps_out) {
+    const double val = state[0], lo = state[1], dur = state[2];
+    *eps_out = (float)val;
+    state[0] = fmax(lo, __dsub_rn(val, __ddiv_rn(__dsub_rn(val, lo), dur)));
+}
+
 }  // namespace
 
 extern "C" int dtqn_version(void) { return DTQN_ABI_VERSION; }
+
+extern "C" int dtqn_eps_anneal(double* state, float* eps_out, void* stream) {
+    if (!state || !eps_out) return DTQN_E_ARG;
+    eps_anneal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, eps_out);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int dtqn_env_reset_all(const dtqn_env* env, const dtqn_replay* rb, const dtqn_context* cx, void* stream) {
     int rc = check_env(env, rb, cx);

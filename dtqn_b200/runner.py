@@ -1,6 +1,7 @@
 """Batched training loop -- the shape of run.train / run.step / run.prepopulate / run.evaluate (run.py:187-405) for
 n_envs lockstep device environments per GPU, data-parallel over ranks (one process per GPU): envs and replay are
 sharded per rank, parameters replicated, one gradient allreduce per update (agents.DtqnAgent.train_on_windows)."""
+import ctypes as C
 from typing import Optional
 
 import torch
@@ -53,7 +54,8 @@ class BatchedTrainer:
         self.n_envs = n_envs
         self.iterations = 0
         self._graph = None
-        self._eps_pinned = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        # exploration schedule mirrored on the device: a replayed graph reads / anneals it without any host write
+        self._eps_state = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._eps_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def prepopulate(self, lockstep_steps: int) -> None:
@@ -64,7 +66,7 @@ class BatchedTrainer:
     def _device_iteration(self) -> None:
         """Everything of one loop iteration that runs on the device before the gradient collective."""
         agent, rb = self.agent, self.agent.replay_buffer
-        self._eps_dev.copy_(self._eps_pinned, non_blocking=True)
+        self._device_epsilon()
         agent.act_and_step(self.env, 0.0, epsilon_dev=self._eps_dev)
         eps, starts = rb.draw_indices(agent.batch_size)
         rb.gather_windows(eps, starts, out=agent._win)
@@ -72,13 +74,21 @@ class BatchedTrainer:
         if self._update_in_graph:
             agent.reduce_and_step()
 
+    def _sync_epsilon_to_device(self) -> None:
+        self._eps_state.copy_(torch.tensor([self.eps.val, getattr(self.eps, "min", self.eps.val),
+                                            getattr(self.eps, "duration", 1)], dtype=torch.float64))
+
+    def _device_epsilon(self) -> None:
+        _lib.check(_lib.lib.dtqn_eps_anneal(C.c_void_p(self._eps_state.data_ptr()), C.c_void_p(self._eps_dev.data_ptr()),
+                                            _lib.stream_ptr()), "dtqn_eps_anneal")
+
     def enable_graphs(self) -> None:
         """Capture one loop iteration (acting forward, env step + roll, sample, gather, 3 forwards, TD, backward and --
         single GPU -- clip + Adam) into a CUDA graph: ~60 launches replayed with one host call.  The per-step scalars
         (epsilon, Adam step, sampler draw counter) live in device memory so the replay needs no re-capture."""
         assert self.agent.replay_buffer.can_sample(self.agent.batch_size), "prepopulate before capturing"
         self.agent.eval_off()
-        self._eps_pinned[0] = float(self.eps.val)
+        self._sync_epsilon_to_device()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                     # warm-up on a side stream (allocations, lazy module loads)
@@ -113,7 +123,7 @@ class BatchedTrainer:
 
     def act_only(self) -> None:
         """Acting half of an iteration: acting forward + eps-greedy + env step / append / roll."""
-        self._eps_dev.copy_(self._eps_pinned, non_blocking=True)
+        self._device_epsilon()
         self.agent.act_and_step(self.env, 0.0, epsilon_dev=self._eps_dev)
 
     def train_only(self) -> None:
@@ -127,7 +137,6 @@ class BatchedTrainer:
     def train_iteration(self) -> None:
         """One iteration of the run.train loop body (run.py:290-298) for all envs: step, train, anneal."""
         if self._graph is not None:
-            self._eps_pinned[0] = float(self.eps.val)
             self._graph.replay()
             if not self._update_in_graph:
                 self.agent.reduce_and_step()

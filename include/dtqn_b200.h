@@ -108,6 +108,11 @@ typedef struct dtqn_step_io {
 
 int dtqn_version(void);
 
+/* Exploration schedule on the device (LinearAnneal.anneal, utils/epsilon_anneal.py:33-34; run.py:298): writes the current
+ * value to *eps_out (the `epsilon_dev` of the next dtqn_env_step) and advances state = {val, min, duration} (3 doubles,
+ * device memory) by val <- max(min, val - (val - min) / duration) in double precision, bit-identical to the host loop. */
+int dtqn_eps_anneal(double* state, float* eps_out, void* stream);
+
 /* env.reset() of every instance + agent.context_reset(obs) (run.py:287-288): allocates slots 0..n-1, stores the first
  * observation (ReplayBuffer.store_obs :88-92) and resets the contexts.  rb / cx may be NULL. */
 int dtqn_env_reset_all(const dtqn_env* env, const dtqn_replay* rb, const dtqn_context* cx, void* stream);

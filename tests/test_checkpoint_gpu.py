@@ -83,6 +83,8 @@ def test_resume_continues_like_the_uninterrupted_run(tmp_path, graphs):
                    td=ag.td_errors.mean(), ctx=ag.train_context.obs.clone())
     else:
         rb_ = finish(b)
+    if graphs:                            # the device-side exploration schedule tracks the host LinearAnneal bit for bit
+        assert float(a._eps_state[0].item()) == a.eps.val and float(b._eps_state[0].item()) == b.eps.val
     for k in ("counters", "lens", "obss", "ctx"):
         assert torch.equal(ra[k], rb_[k]), k
     assert np.array_equal(ra["rng"], rb_["rng"])
