@@ -10,6 +10,7 @@
 #include "gemm_simt.cuh"
 #include "prof.cuh"
 #include "linear_tc.cuh"
+#include "attn_mma.cuh"
 
 namespace {
 
@@ -387,6 +388,38 @@ attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, int
     }
 }
 
+// ---- causal self-attention on the warp-level tensor cores (mma.sync TF32 x3), one CTA per sequence, warp = head ----------------
+// d_model = 64, 8 heads of 8, L <= 64.  The sequence's packed qkv rows are staged once in shared memory (coalesced float4 loads,
+// q pre-scaled for the base-2 softmax); every warp runs att_head() for its head and parks the normalised outputs in the q
+// columns it has just consumed, so the result leaves as full 256-byte rows.
+__global__ void __launch_bounds__(256)
+attn_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, float scale) {
+    extern __shared__ float sm_kv[];                           // [64][ATT_LD]
+    const size_t t0 = (size_t)blockIdx.x * L;
+    const int tid = threadIdx.x;
+    const float qs = scale * 1.4426950408889634f;
+    for (int e = tid; e < 64 * 48; e += 256) {
+        const int r = e / 48, c4 = (e % 48) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < L) {
+            v = __ldg(reinterpret_cast<const float4*>(qkv + (t0 + r) * 192 + c4));
+            if (c4 < 64) { v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs; }
+        }
+        *reinterpret_cast<float4*>(sm_kv + r * ATT_LD + c4) = v;
+    }
+    __syncthreads();
+    const int h = tid >> 5, lane = tid & 31;
+    float* sq = sm_kv;
+    att_head(sq, h, L, lane, [&](int row, int col, float v0, float v1) {
+        *reinterpret_cast<float2*>(sq + row * ATT_LD + col) = make_float2(v0, v1);
+    });
+    __syncthreads();
+    for (int e = tid; e < L * 16; e += 256) {
+        const int r = e >> 4, c4 = (e & 15) * 4;
+        *reinterpret_cast<float4*>(o + (t0 + r) * 64 + c4) = *reinterpret_cast<const float4*>(sm_kv + r * ATT_LD + c4);
+    }
+}
+
 // ---- acting: attention of the LAST valid query only (the policy reads q[:, -1, :], agents/dtqn.py:107) ------------------
 // ql [G*n_seq, d] = scaled-later query of the last valid token; kv [T, 2d] = (k | v) of every token.  One warp per
 // (sequence, head): lanes stride over the n_i keys, warp-shuffle softmax, then HD warp reductions for P V.
@@ -550,6 +583,8 @@ extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_
 // tensor cores) and the exact-fp32 forward keeps ReLU masks -- hence gradients -- closest to the reference's.
 static int g_tc_min_tokens = 4096;
 static int g_seq_fused = 1;
+static int g_attn_mma = 1;        // mma.sync TF32x3 attention core for d = 64 / 8 heads / L <= 64 (0: fp32 CUDA-core kernel)
+extern "C" int dtqn_set_attn_mma(int32_t on) { g_attn_mma = on; return 0; }
 static int g_tc_fuse_embed = 0;   // measured slower (dependent timestep -> obs -> pos loads stall the producers): off by default
 extern "C" int dtqn_set_tc_fuse_embed(int32_t on) { g_tc_fuse_embed = on; return 0; }
 extern "C" int dtqn_set_seq_fused(int32_t on) { g_seq_fused = on; return 0; }
@@ -631,7 +666,15 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
             const size_t smem = sizeof(float) * 2 * (size_t)(L + 4) * (d + 4);
             const bool seq_kernel = H * 32 <= 256 && (hd == 8 || hd == 16);
             prof_begin(PROF_ATTN_FWD, st);
-            if (seq_kernel) {
+            if (g_attn_mma && seq_kernel && hd == 8 && d == 64 && H == 8 && L <= 64) {
+                const size_t sm_mma = sizeof(float) * 64 * ATT_LD;
+                static bool attr_set = false;
+                if (!attr_set) {
+                    cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+                    attr_set = true;
+                }
+                attn_mma_kernel<<<(unsigned)(n_seq * G), 256, sm_mma, st>>>(la.qkv, la.o, L, scale);
+            } else if (seq_kernel) {
                 if (hd == 8) {
                     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attn_seq_kernel<8><<<(unsigned)(n_seq * G), 32 * H, smem, st>>>(la.qkv, la.o, L, d, scale);

@@ -200,6 +200,9 @@ int dtqn_set_tc_fuse_embed(int32_t on);
 /* 1 (default): on the tcgen05 path (d_model 64, inference) ffn.0 -> ReLU -> ffn.2 -> ReLU -> +residual -> LayerNorm run as
  * ONE kernel with the hidden activations kept in TMEM / shared memory; 0: two Linear launches. */
 int dtqn_set_tc_fuse_ffn(int32_t on);
+/* 1 (default): the attention core of d_model 64 / 8 heads / L <= 64 groups outside the sequence-resident kernel (the acting
+ * forward) runs on the warp-level tensor cores (mma.sync TF32 hi/lo split); 0: fp32 CUDA-core kernel. */
+int dtqn_set_attn_mma(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 

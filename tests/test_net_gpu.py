@@ -286,3 +286,37 @@ def test_train_step_ablation_flags_vs_oracle(pos, history):
         assert float((new[k].cpu() - tr.policy[k]).abs().max()) < 3e-5, k
     if pos != "learned":      # the fixed table is untouched by the optimiser
         assert torch.equal(new["position_embedding.position_encoding"].cpu(), sd["position_embedding.position_encoding"])
+
+
+@pytest.mark.parametrize("L", [1, 7, 16, 17, 50])
+def test_attention_mma_vs_oracle(golden_dir, L):
+    """The mma.sync TF32 hi/lo attention core against the fp32 CPU oracle and against the fp32 CUDA-core kernel, with the
+    in_proj weights scaled up so the softmax is peaked (large scores are where a plain-TF32 product would show)."""
+    from dtqn_b200 import networks, _lib
+    from oracle import network as onet
+    z = np.load(os.path.join(golden_dir, "forward_carflag.npz"))
+    net = _make_net(z, "policy/", "carflag")
+    sd = {k: v.float() for k, v in _sd(z, "policy/").items()}
+    for k in sd:
+        if k.endswith("attention.in_proj_weight"):
+            sd[k] = sd[k] * 25.0
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.empty(37, L, 3).uniform_(-1.1, 1.1, generator=g)
+    with torch.no_grad():
+        ref = onet.forward(sd, x, 8).numpy()
+    networks.set_tc_min_tokens(1 << 30)
+    _lib.lib.dtqn_set_seq_fused(0)               # general path: one kernel per GEMM / attention
+    try:
+        _lib.lib.dtqn_set_attn_mma(1)
+        q_mma = net(x).cpu().numpy()
+        _lib.lib.dtqn_set_attn_mma(0)
+        q_simt = net(x).cpu().numpy()
+    finally:
+        _lib.lib.dtqn_set_attn_mma(1)
+        _lib.lib.dtqn_set_seq_fused(1)
+        networks.set_tc_min_tokens(4096)
+    e_mma, e_simt = rel_err(q_mma, ref), rel_err(q_simt, ref)
+    print(f"L={L}: rel err mma {e_mma:.3e}  cuda-core {e_simt:.3e}")
+    assert e_simt < Q_REL_TIGHT
+    assert e_mma < Q_REL_TIGHT, e_mma
