@@ -270,7 +270,7 @@ def main():
     if rank == 0:
         tags = {}
         names = ["linear_fwd", "attn_fwd", "env_step", "env_roll", "replay_gather", "dgrad", "wgrad", "attn_bwd", "ln_bwd",
-                 "embed", "head", "td_loss", "clip_adam", "other", "linear_tcgen05", "seq_fused_fwd"]
+                 "embed", "head", "td_loss", "clip_adam", "other", "linear_tcgen05", "seq_fused_fwd", "act_fused_tcgen05"]
         for t, nm in enumerate(names):
             ms_t, n_t, w_t = C.c_double(), C.c_int64(), C.c_double()
             lib.dtqn_profile_read(t, C.byref(ms_t), C.byref(n_t), C.byref(w_t))
@@ -281,7 +281,7 @@ def main():
         dom = max(tags.items(), key=lambda kv: kv[1]["ms"]) if tags else None
         if dom is not None:
             nm, v = dom
-            tensor = nm in ("linear_fwd", "dgrad", "wgrad", "attn_fwd", "attn_bwd", "seq_fused_fwd")
+            tensor = nm in ("linear_fwd", "dgrad", "wgrad", "attn_fwd", "attn_bwd", "seq_fused_fwd", "act_fused_tcgen05")
             if tensor:
                 ach = v["work"] / (v["ms"] * 1e-3) / 1e12
                 roof = {"kernel": nm, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

@@ -1,0 +1,528 @@
+// Fused acting forward of the 2-layer DTQN (DtqnAgent.get_action, dtqn/agents/dtqn.py:81-107 -> DTQN.forward,
+// dtqn/networks/dtqn.py:181-216) for n_envs lockstep context windows: ONE persistent tcgen05 kernel takes the context
+// ring to the two per-sequence vectors the rest of the final layer needs.  Per 128-row tile (two sequences of L <= 52
+// tokens) every intermediate stays on the SM:
+//
+//   obs rows (context ring, utils/context.py window)  --embed (Linear(O,64) + position table, dtqn.py:181-199)-->  x0
+//   x0 --in_proj (MMA)--> qkv (TMEM -> smem fp32) --causal attention (mma.sync TF32 hi/lo, attn_mma.cuh)--> o
+//   o  --out_proj (MMA) -> ReLU -> +x0 -> LayerNorm1--> x1 --ffn.0 (MMA) -> ReLU -> ffn.2 (MMA) -> ReLU -> +x1 -> LayerNorm2--> x2
+//   x2 --layer-1 in_proj (MMA)--> q | k | v --attention row of the LAST valid position only--> o_last
+//                                                                                (transformer.py:63-78, causal mask :49-53)
+// Outputs per sequence: x2[last] (residual of the final layer's LayerNorm1) and o_last; the n_seq-row remainder of the
+// final layer and the Q head run on those (dtqn_forward).  HBM traffic per token: the 12-byte observation row in, nothing
+// out -- against ~5.6 KB of fp32 activations per token for the kernel-per-GEMM path.
+//
+// Roles (576 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-15  workers: embed, TMEM epilogues (thread = row, 16 columns each; LayerNorm reduced through smem),
+//               attention (warp = (sequence, head)), bf16 hi/lo split into the K-major A operand
+//   warp 16     lane 0 issues every tcgen05.mma (M = 128, N = 64, bf16 hi/lo split: 3 MMAs per k-step) + commits
+//   warp 17     lane 0 streams the weight image (15 chunks of 16 KB per tile: [64 x 64] hi + lo, consumption order)
+//               through a 3-slot ring with cp.async.bulk (TMA) + mbarrier complete_tx
+// TMEM (512 columns): [0,256) in_proj / ffn.0 / layer-1 in_proj accumulators, [256,320) out_proj, [320,384) ffn.2.
+#include "net.cuh"
+#include "prof.cuh"
+#include "linear_tc.cuh"
+#include "tc_common.cuh"
+#include "attn_mma.cuh"
+
+namespace {
+
+constexpr int AF_WORKERS = 512;
+constexpr int AF_THREADS = AF_WORKERS + 64;
+constexpr int AF_NCHUNK = 15;                     // weight chunks per tile
+constexpr int AF_WSLOTS = 3;
+constexpr uint32_t AF_WCHUNK = 64 * TC_KC * 4;    // [64 x 64] hi + lo
+constexpr int AF_QKV_ROWS = 116;                  // rows of the staged q|k|v tile (L + 64 <= 116)
+constexpr int AF_XLD = 68;                        // fp32 residual tile row stride (floats): conflict-free float4 per row
+constexpr int AF_MAX_L = 52;
+constexpr uint32_t AF_R_BYTES = AF_QKV_ROWS * ATT_LD * 4;      // q|k|v tile; the 2-stage hidden-operand ring aliases it
+static_assert(AF_R_BYTES >= 2 * A_STAGE_BYTES, "hidden operand ring must fit in the qkv region");
+
+// parameter vectors staged in shared memory (float offsets)
+enum { P_INB0 = 0, P_OUTB0 = 192, P_LN1W = 256, P_LN1B = 320, P_F1B = 384, P_F2B = 640, P_LN2W = 704, P_LN2B = 768,
+       P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_TOTAL = 1344 };
+
+enum { B_W_FULL = 0, B_W_EMPTY = 3, B_AX0 = 6, B_AO = 7, B_AX1 = 8, B_AX2 = 9, B_ACC_QKV = 10, B_ACC_OUT = 11,
+       B_ACC1 = 12 /* +c */, B_ACC_F2 = 16, B_ACC_L1 = 17, B_A2_FULL = 18 /* +s */, B_A2_EMPTY = 20 /* +s */, B_COUNT = 22 };
+
+constexpr size_t AF_SMEM = 1024 + AF_WSLOTS * AF_WCHUNK + A_STAGE_BYTES + AF_R_BYTES +
+                           128 * AF_XLD * 4 + P_TOTAL * 4 + 2 * 128 * 4 * 4 + 2 * 128 * 4 * 4 + 16 + 256 + B_COUNT * 8 + 16;
+static_assert(AF_SMEM <= 227 * 1024, "fused acting forward: shared memory budget");
+
+struct ActFusedArgs {
+    GroupPtrs P;
+    GroupSrc S;
+    const uint8_t* img[DTQN_MAX_GROUPS];           // 15-chunk weight image of each group's network
+    long long emb_w, emb_b, pos;
+    LayerOff l0, l1;
+    int O, n_seq, L;
+    float obs_mask;
+    float* xl;                                     // [G * n_seq, 64]  x2 at the last valid position
+    float* ol;                                     // [G * n_seq, 64]  final-layer attention output of that position
+};
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(AF_WORKERS) : "memory"); }
+
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 12 MMAs: D[128 x 64] (+)= A[128 x 64] W[64 x 64]^T with the bf16 hi/lo split (hi*hi + hi*lo + lo*hi)
+__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint32_t a_u, uint32_t b_u, uint32_t idesc, bool acc_first) {
+#pragma unroll
+    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
+        const uint64_t a_hi = umma_desc(a_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+        const uint64_t a_lo = umma_desc(a_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
+        const uint64_t b_hi = umma_desc(b_u + k16 * 2 * (64 * 16), 64 * 16, 128);
+        const uint64_t b_lo = umma_desc(b_u + AF_WCHUNK / 2 + k16 * 2 * (64 * 16), 64 * 16, 128);
+        umma_bf16(d_tmem, a_hi, b_hi, idesc, (acc_first || k16) ? 1u : 0u);
+        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 1)
+act_fused_kernel(ActFusedArgs t) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const int L = t.L;
+
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW = base;                                            // weight ring
+    uint8_t* sA = sW + AF_WSLOTS * AF_WCHUNK;                      // A operand (K = 64): x0 -> o -> x1 -> x2
+    uint8_t* sR = sA + A_STAGE_BYTES;
+    float* sQKV = reinterpret_cast<float*>(sR);                    // [AF_QKV_ROWS][ATT_LD]
+    uint8_t* sA2 = sR;                                             // hidden operand ring (2 stages), aliases sQKV
+    float* sX = reinterpret_cast<float*>(sR + AF_R_BYTES);         // [128][AF_XLD] fp32 residual (x0, then x1)
+    float* sPar = sX + 128 * AF_XLD;
+    float* sRedA = sPar + P_TOTAL;                                 // [128][4] LayerNorm partial sums
+    float* sRedB = sRedA + 128 * 4;
+    float* sObs = sRedB + 128 * 4;                                 // [2][128][4] observation rows of the tile (double buffered)
+    int* sMeta = reinterpret_cast<int*>(sObs + 2 * 128 * 4);       // [2][2] valid length of the tile's two sequences
+    uint8_t* sFlag = reinterpret_cast<uint8_t*>(sMeta + 4);        // [2][128] 1 = row belongs to a real sequence
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sFlag + 256);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    volatile int* s_fail = reinterpret_cast<volatile int*>(s_tmem + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // bounded wait that never makes a role skip a hand-off: after the first time-out everybody free-runs to the end
+    auto WAIT = [&](int b, uint32_t parity) {
+        if (*s_fail) return;
+        if (!mbar_wait(BAR(b), parity)) *s_fail = 1;
+    };
+
+    const float* p = t.P.p[g];
+    for (int e = tid; e < P_TOTAL; e += AF_THREADS) {
+        float v;
+        if (e < P_OUTB0) v = __ldg(p + t.l0.in_b + e);
+        else if (e < P_LN1W) v = __ldg(p + t.l0.out_b + (e - P_OUTB0));
+        else if (e < P_LN1B) v = __ldg(p + t.l0.ln1_w + (e - P_LN1W));
+        else if (e < P_F1B) v = __ldg(p + t.l0.ln1_b + (e - P_LN1B));
+        else if (e < P_F2B) v = __ldg(p + t.l0.f1_b + (e - P_F1B));
+        else if (e < P_LN2W) v = __ldg(p + t.l0.f2_b + (e - P_F2B));
+        else if (e < P_LN2B) v = __ldg(p + t.l0.ln2_w + (e - P_LN2W));
+        else if (e < P_INB1) v = __ldg(p + t.l0.ln2_b + (e - P_LN2B));
+        else if (e < P_EW) v = __ldg(p + t.l1.in_b + (e - P_INB1));
+        else if (e < P_EB) { const int c = (e - P_EW) >> 2, k = (e - P_EW) & 3; v = k < t.O ? __ldg(p + t.emb_w + c * t.O + k) : 0.f; }
+        else v = __ldg(p + t.emb_b + (e - P_EB));
+        sPar[e] = v;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < AF_WSLOTS; ++s) { mbar_init(BAR(B_W_FULL + s), 1); mbar_init(BAR(B_W_EMPTY + s), 1); }
+        mbar_init(BAR(B_AX0), AF_WORKERS); mbar_init(BAR(B_AO), AF_WORKERS);
+        mbar_init(BAR(B_AX1), AF_WORKERS); mbar_init(BAR(B_AX2), AF_WORKERS);
+        mbar_init(BAR(B_ACC_QKV), 1); mbar_init(BAR(B_ACC_OUT), 1); mbar_init(BAR(B_ACC_F2), 1); mbar_init(BAR(B_ACC_L1), 1);
+        for (int c = 0; c < 4; ++c) mbar_init(BAR(B_ACC1 + c), 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(BAR(B_A2_FULL + s), AF_WORKERS); mbar_init(BAR(B_A2_EMPTY + s), 1); }
+        *s_fail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    constexpr uint32_t TM_OUT = 256, TM_F2 = 320;
+
+    const int tiles = (t.n_seq + 1) >> 1;
+    const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < 16) {
+        // =============================================== workers ===============================================
+        const int q4 = warp & 3, cq = warp >> 2;
+        const int row = q4 * 32 + lane, c0 = cq * 16;
+        const int sl = row >= 2 * L ? 2 : (row >= L ? 1 : 0);      // which of the tile's sequences this row belongs to (2: padding)
+        const int jrow = row - sl * L;
+        const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+        const dtqn_obs_src& src = t.S.s[g];
+        const float qs = 0.35355339059327373f * 1.4426950408889634f;   // log2(e) / sqrt(head_dim = 8)
+        const bool loader = cq == 0;                               // warps 0-3: one thread per tile row fetches its observation
+
+        // observation row of `row` in tile `tile` (context window position jrow of sequence 2*tile + sl)
+        int pf_ts = 0;
+        auto obs_ts = [&](int tile) {                              // stage 1: the sequence's timestep
+            const int seq = tile * 2 + sl;
+            pf_ts = (sl < 2 && seq < t.n_seq && src.timestep) ? __ldg(src.timestep + seq) : 0;
+        };
+        float pf_o[4]; int pf_flag = 0, pf_n = 0;
+        auto obs_rows = [&](int tile) {                            // stage 2: the ring row (depends on the timestep)
+            const int seq = tile * 2 + sl;
+            pf_o[0] = pf_o[1] = pf_o[2] = pf_o[3] = 0.f; pf_flag = 0; pf_n = 0;
+            if (sl < 2 && seq < t.n_seq) {
+                int rr = jrow; bool ok = true; pf_n = L;
+                if (src.timestep) {
+                    const int n = min(src.ring_len, pf_ts + 1);
+                    ok = jrow < n;
+                    rr = ok ? (pf_ts + 1 - n + jrow) % src.ring_len : 0;
+                    pf_n = min(n, L);
+                }
+                const float* o = src.obs + (long long)seq * src.seq_stride + (long long)rr * t.O;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < t.O) pf_o[k] = ok ? __ldg(o + k) : t.obs_mask;
+                pf_flag = 1;
+            }
+        };
+        auto obs_store = [&](int buf) {                            // stage 3: publish in shared memory
+            *reinterpret_cast<float4*>(sObs + (buf * 128 + row) * 4) = make_float4(pf_o[0], pf_o[1], pf_o[2], pf_o[3]);
+            sFlag[buf * 128 + row] = (uint8_t)pf_flag;
+            if (sl < 2 && jrow == 0) sMeta[buf * 2 + sl] = pf_n;
+        };
+        // two 8-column groups of this thread's 16 columns -> bf16 hi/lo in the canonical K-major layout
+        auto store_a = [&](uint8_t* dstA, const float (&y)[16]) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                float x8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x8[e] = y[hlf * 8 + e];
+                uint4 hi, lo;
+                split8(x8, hi, lo);
+                uint8_t* d = dstA + (cq * 2 + hlf) * A_CHUNK_STRIDE + row * 16;
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + A_HALF_BYTES) = lo;
+            }
+        };
+        // accumulator [128 x 192] (+ in_proj bias, q columns pre-scaled for the base-2 softmax) -> staged fp32 q|k|v tile
+        auto dump_qkv = [&](int bias_off) {
+            uint32_t r[3][16];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) tmem_ld16_issue(tlane + (uint32_t)(cq * 48 + cc * 16), r[cc]);
+            tmem_ld_wait();
+            tc_fence_before();
+            if (row < AF_QKV_ROWS) {
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    const int col = cq * 48 + cc * 16;
+                    const float sc = col < 64 ? qs : 1.f;
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sPar + bias_off + col + q);
+                        *reinterpret_cast<float4*>(sQKV + row * ATT_LD + col + q) =
+                            make_float4((__uint_as_float(r[cc][q]) + b.x) * sc, (__uint_as_float(r[cc][q + 1]) + b.y) * sc,
+                                        (__uint_as_float(r[cc][q + 2]) + b.z) * sc, (__uint_as_float(r[cc][q + 3]) + b.w) * sc);
+                    }
+                }
+            }
+        };
+        // y = LayerNorm(x_res + relu(acc + b)) over the 64 columns of `row` (4 threads x 16 columns, reduced through smem);
+        // y replaces the residual tile row and becomes the next A operand
+        auto res_ln = [&](uint32_t tm_col, int b_off, int gw_off, int gb_off, float (&y)[16]) {
+            float v[16];
+            tmem_ld16(tlane + tm_col + (uint32_t)c0, v);
+            tc_fence_before();
+            float* xr = sX + row * AF_XLD + c0;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xr + q);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { y[q + e] = xv[e] + fmaxf(v[q + e] + sPar[b_off + c0 + q + e], 0.f); s += y[q + e]; }
+            }
+            sRedA[row * 4 + cq] = s;
+            worker_bar();
+            const float4 ra = *reinterpret_cast<const float4*>(sRedA + row * 4);
+            const float mean = ((ra.x + ra.y) + (ra.z + ra.w)) * (1.f / 64.f);
+            float vs = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { const float dl = y[e] - mean; vs = fmaf(dl, dl, vs); }
+            sRedB[row * 4 + cq] = vs;
+            worker_bar();
+            const float4 rb = *reinterpret_cast<const float4*>(sRedB + row * 4);
+            const float rstd = 1.0f / sqrtf(((rb.x + rb.y) + (rb.z + rb.w)) * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] = (y[e] - mean) * rstd * sPar[gw_off + c0 + e] + sPar[gb_off + c0 + e];
+        };
+
+        if (my_tiles > 0 && loader) { obs_ts((int)blockIdx.x); obs_rows((int)blockIdx.x); obs_store(0); }
+        worker_bar();
+
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tile_next = tile + (int)gridDim.x;
+            const bool has_next = i + 1 < my_tiles;
+            const uint32_t ph = (uint32_t)(i & 1);
+            const int buf = i & 1;
+
+            // ---- token embedding: x0 = W_e obs + b_e + pos[j]  (rows outside a real sequence: 0) ----
+            {
+                const float4 o4 = *reinterpret_cast<const float4*>(sObs + (buf * 128 + row) * 4);
+                const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
+                const bool real = sFlag[buf * 128 + row] != 0;
+                float y[16];
+#pragma unroll
+                for (int q = 0; q < 16; q += 4) {
+                    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (real) pv = __ldg(reinterpret_cast<const float4*>(p + t.pos + (long long)jrow * 64 + c0 + q));
+                    const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float acc = sPar[P_EB + c0 + q + e];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc = fmaf(ov[k], sPar[P_EW + (c0 + q + e) * 4 + k], acc);
+                        y[q + e] = real ? acc + pvv[e] : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(sX + row * AF_XLD + c0 + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                }
+                store_a(sA, y);
+                fence_async_smem();
+                mbar_arrive(BAR(B_AX0));
+            }
+            // ---- layer-0 q|k|v: TMEM -> shared memory ----
+            WAIT(B_ACC_QKV, ph);
+            tc_fence_after();
+            dump_qkv(P_INB0);
+            if (has_next && loader) obs_ts(tile_next);
+            worker_bar();
+            // ---- causal attention, warp = (sequence, head); o -> A operand ----
+            {
+                const int s = warp >> 3, h = warp & 7;
+                const int n = sMeta[buf * 2 + s];
+                if (n > 0) {
+                    const int rbase = s * L;
+                    att_head(sQKV + rbase * ATT_LD, h, n, lane, [&](int r, int col, float v0, float v1) {
+                        if (r < n) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                            uint8_t* d = sA + (col >> 3) * A_CHUNK_STRIDE + (rbase + r) * 16 + (col & 7) * 2;
+                            *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(h0, h1);
+                            *reinterpret_cast<uint32_t*>(d + A_HALF_BYTES) = pack_bf16x2(l0, l1);
+                        }
+                    });
+                }
+                if (has_next && loader) obs_rows(tile_next);
+                fence_async_smem();
+                mbar_arrive(BAR(B_AO));
+            }
+            // ---- out_proj -> ReLU -> +x0 -> LayerNorm1 -> x1 ----
+            WAIT(B_ACC_OUT, ph);
+            tc_fence_after();
+            if (has_next && loader) obs_store(buf ^ 1);
+            {
+                float y[16];
+                res_ln(TM_OUT, P_OUTB0, P_LN1W, P_LN1B, y);
+#pragma unroll
+                for (int q = 0; q < 16; q += 4)
+                    *reinterpret_cast<float4*>(sX + row * AF_XLD + c0 + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                store_a(sA, y);
+                fence_async_smem();
+                mbar_arrive(BAR(B_AX1));
+            }
+            // ---- ffn.0 accumulator chunk c -> +b1 -> ReLU -> hi/lo -> hidden operand ring ----
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int m = 2 * i + (c >> 1), s_ = c & 1;
+                WAIT(B_ACC1 + c, ph);
+                tc_fence_after();
+                float v[16];
+                tmem_ld16(tlane + (uint32_t)(c * 64 + c0), v);
+                tc_fence_before();
+                if (m >= 1) WAIT(B_A2_EMPTY + s_, (uint32_t)((m - 1) & 1));
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e] + sPar[P_F1B + c * 64 + c0 + e], 0.f);
+                store_a(sA2 + s_ * A_STAGE_BYTES, v);
+                fence_async_smem();
+                mbar_arrive(BAR(B_A2_FULL + s_));
+            }
+            // ---- ffn.2 -> ReLU -> +x1 -> LayerNorm2 -> x2 ----
+            WAIT(B_ACC_F2, ph);
+            tc_fence_after();
+            {
+                float y[16];
+                res_ln(TM_F2, P_F2B, P_LN2W, P_LN2B, y);
+                store_a(sA, y);
+                if (sl < 2) {
+                    const int n = sMeta[buf * 2 + sl];
+                    if (n > 0 && jrow == n - 1) {                  // residual of the final layer's LayerNorm1
+                        float* dst = t.xl + ((long long)g * t.n_seq + tile * 2 + sl) * 64 + c0;
+#pragma unroll
+                        for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(BAR(B_AX2));
+            }
+            // ---- final layer: q|k|v -> shared memory, attention row of the last valid position ----
+            WAIT(B_ACC_L1, ph);
+            tc_fence_after();
+            dump_qkv(P_INB1);
+            worker_bar();
+            {
+                const int s = warp >> 3, h = warp & 7;
+                const int n = sMeta[buf * 2 + s];
+                if (n > 0) {
+                    const float* sb = sQKV + s * L * ATT_LD;
+                    const float4 qa = *reinterpret_cast<const float4*>(sb + (n - 1) * ATT_LD + h * 8);
+                    const float4 qb = *reinterpret_cast<const float4*>(sb + (n - 1) * ATT_LD + h * 8 + 4);
+                    float sc[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int j = lane + 32 * r;
+                        sc[r] = -INFINITY;
+                        if (j < n) {
+                            const float4 ka = *reinterpret_cast<const float4*>(sb + j * ATT_LD + 64 + h * 8);
+                            const float4 kb = *reinterpret_cast<const float4*>(sb + j * ATT_LD + 64 + h * 8 + 4);
+                            float a = qa.x * ka.x;
+                            a = fmaf(qa.y, ka.y, a); a = fmaf(qa.z, ka.z, a); a = fmaf(qa.w, ka.w, a);
+                            a = fmaf(qb.x, kb.x, a); a = fmaf(qb.y, kb.y, a); a = fmaf(qb.z, kb.z, a); a = fmaf(qb.w, kb.w, a);
+                            sc[r] = a;
+                        }
+                    }
+                    const float mx = warp_max_f(fmaxf(sc[0], sc[1]));
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, l = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int j = lane + 32 * r;
+                        if (j < n) {
+                            const float pj = att_ex2(sc[r] - mx);
+                            l += pj;
+                            const float4 va = *reinterpret_cast<const float4*>(sb + j * ATT_LD + 128 + h * 8);
+                            const float4 vb = *reinterpret_cast<const float4*>(sb + j * ATT_LD + 128 + h * 8 + 4);
+                            acc[0] = fmaf(pj, va.x, acc[0]); acc[1] = fmaf(pj, va.y, acc[1]); acc[2] = fmaf(pj, va.z, acc[2]); acc[3] = fmaf(pj, va.w, acc[3]);
+                            acc[4] = fmaf(pj, vb.x, acc[4]); acc[5] = fmaf(pj, vb.y, acc[5]); acc[6] = fmaf(pj, vb.z, acc[6]); acc[7] = fmaf(pj, vb.w, acc[7]);
+                        }
+                    }
+                    l = warp_sum_f(l);
+                    float mine = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float a = warp_sum_f(acc[c]);
+                        if (lane == c) mine = a;
+                    }
+                    if (lane < 8) t.ol[((long long)g * t.n_seq + tile * 2 + s) * 64 + h * 8 + lane] = mine / l;
+                }
+            }
+        }
+    } else if (warp == 16) {
+        // =============================================== MMA issuer ===============================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_M, 64);
+            const uint32_t sA_u = smem_u32(sA), sA2_u = smem_u32(sA2), sW_u = smem_u32(sW);
+            int n = 0;                                             // running weight-chunk counter (ring position)
+            auto wslot = [&]() -> uint32_t {                       // wait for chunk n, return its smem address
+                WAIT(B_W_FULL + n % AF_WSLOTS, (uint32_t)((n / AF_WSLOTS) & 1));
+                return sW_u + (uint32_t)(n % AF_WSLOTS) * AF_WCHUNK;
+            };
+            auto wdone = [&]() { umma_commit(BAR(B_W_EMPTY + n % AF_WSLOTS)); ++n; };
+            for (int i = 0; i < my_tiles; ++i) {
+                const uint32_t ph = (uint32_t)(i & 1);
+                WAIT(B_AX0, ph);
+                tc_fence_after();
+                for (int c = 0; c < 3; ++c) { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone(); }
+                umma_commit(BAR(B_ACC_QKV));
+                WAIT(B_AO, ph);
+                tc_fence_after();
+                { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + TM_OUT, sA_u, b, idesc, false); wdone(); }
+                umma_commit(BAR(B_ACC_OUT));
+                WAIT(B_AX1, ph);
+                tc_fence_after();
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t b = wslot(); tc_fence_after();
+                    mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone();
+                    umma_commit(BAR(B_ACC1 + c));
+                }
+                for (int c = 0; c < 4; ++c) {
+                    const int m = 2 * i + (c >> 1), s_ = c & 1;
+                    WAIT(B_A2_FULL + s_, (uint32_t)(m & 1));
+                    const uint32_t b = wslot(); tc_fence_after();
+                    mma_chunk(tmem + TM_F2, sA2_u + (uint32_t)s_ * A_STAGE_BYTES, b, idesc, c > 0); wdone();
+                    umma_commit(BAR(B_A2_EMPTY + s_));
+                }
+                umma_commit(BAR(B_ACC_F2));
+                WAIT(B_AX2, ph);
+                tc_fence_after();
+                for (int c = 0; c < 3; ++c) { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone(); }
+                umma_commit(BAR(B_ACC_L1));
+            }
+        }
+    } else {
+        // =============================================== weight producer ===============================================
+        if (lane == 0) {
+            const uint8_t* img = t.img[g];
+            const int total = my_tiles * AF_NCHUNK;
+            for (int n = 0; n < total; ++n) {
+                const int s = n % AF_WSLOTS, use = n / AF_WSLOTS;
+                if (use >= 1) WAIT(B_W_EMPTY + s, (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(BAR(B_W_FULL + s), AF_WCHUNK);
+                bulk_g2s(smem_u32(sW) + (uint32_t)s * AF_WCHUNK, img + (size_t)(n % AF_NCHUNK) * AF_WCHUNK, AF_WCHUNK, BAR(B_W_FULL + s));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+}  // namespace
+
+static int g_act_fused = 1;
+extern "C" int dtqn_set_act_fused(int32_t on) { g_act_fused = on; return 0; }
+
+bool act_fused_supported(const dtqn_net_cfg& c, int L) {
+    return g_act_fused && c.n_layers == 2 && c.d_model == 64 && c.n_heads == 8 && !c.discrete && c.obs_dim <= 4 && L >= 3 &&
+           L <= AF_MAX_L;
+}
+
+int launch_act_fused(const dtqn_net_cfg& c, const NetLayout& lay, const GroupPtrs& P, const GroupSrc& S, int G,
+                     const uint8_t* const* packed, long long img_off, int n_seq, int L, float* xl, float* ol, cudaStream_t st) {
+    ActFusedArgs t{};
+    t.P = P; t.S = S;
+    for (int g = 0; g < G; ++g) t.img[g] = packed[g] + img_off;
+    t.emb_w = lay.emb_w; t.emb_b = lay.emb_b; t.pos = lay.pos; t.l0 = lay.layer[0]; t.l1 = lay.layer[1];
+    t.O = c.obs_dim; t.n_seq = n_seq; t.L = L; t.obs_mask = -5.0f; t.xl = xl; t.ol = ol;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(act_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int tiles = (n_seq + 1) / 2;
+    int gx = 148 / G; if (gx < 1) gx = 1; if (gx > tiles) gx = tiles;
+    // algorithmic FLOPs: embed + full layer 0 + layer-1 K|V for every token, layer-1 query + attention row per sequence
+    const double T = (double)G * n_seq * L;
+    const double flops = T * (2.0 * c.obs_dim * 64 + 24.0 * 64 * 64 + 4.0 * L * 64 + 2.0 * 64 * 128) +
+                         (double)G * n_seq * (2.0 * 64 * 64 + 4.0 * L * 64);
+    prof_begin(PROF_ACT_FUSED, st);
+    act_fused_kernel<<<dim3(gx, G, 1), AF_THREADS, AF_SMEM, st>>>(t);
+    prof_end(PROF_ACT_FUSED, st, flops);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+int act_fused_tc_error() {
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
+    return v;
+}

@@ -275,7 +275,6 @@ constexpr int PIPE_THREADS = PIPE_PRODUCERS + 32 + 256;        // 8 epilogue war
 constexpr int STG_COLS = 64;                                   // columns staged per epilogue round
 constexpr int STG_ROW_BYTES = STG_COLS * 4 + 16;               // padded row -> conflict-free 16-byte stores
 constexpr int STG_BYTES = TC_M * STG_ROW_BYTES;
-constexpr int A_STAGE_BYTES = (2 * A_HALF_BYTES + 1023) & ~1023;
 
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -995,6 +994,19 @@ int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab)
         add(lay.layer[i].in_w + (long long)d * d, 2 * d, d);
         add(lay.layer[i].in_w, d, d);
     }
+    // fused acting forward (act_fused.cu): one contiguous image of fifteen [64 x 64] hi+lo chunks in consumption order --
+    // layer-0 in_proj (q, k, v), out_proj, ffn.0 (4 column chunks), ffn.2 (4 k-chunks), layer-1 in_proj (q, k, v)
+    tab.act_img_off = -1;
+    if (c.n_layers == 2 && d == 64) {
+        auto add64 = [&](long long w_off, int N, int K) {
+            TcPackEntry& e = tab.e[n++];
+            e.w_off = w_off; e.N = N; e.K = K; e.n_tile = 64; e.pk_off = off;
+            off += (long long)N * K * 4;
+        };
+        tab.act_img_off = off;
+        add64(lay.layer[0].in_w, 3 * d, d); add64(lay.layer[0].out_w, d, d); add64(lay.layer[0].f1_w, 4 * d, d);
+        add64(lay.layer[0].f2_w, d, 4 * d); add64(lay.layer[1].in_w, 3 * d, d);
+    }
     tab.n = n; tab.total_bytes = off;
     return 0;
 }
@@ -1071,5 +1083,5 @@ extern "C" int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, v
 extern "C" int dtqn_tc_error(void) {
     int v = 0;
     cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int));
-    return v;
+    return v | act_fused_tc_error();
 }

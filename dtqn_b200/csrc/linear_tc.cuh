@@ -3,7 +3,7 @@
 #include "net.cuh"
 
 struct TcPackEntry { long long w_off, pk_off; int N, K, n_tile; };
-struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1]; int n; long long total_bytes; };
+struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1 + 5]; int n; long long total_bytes, act_img_off; };
 
 // entry order: per layer in_proj, out_proj, ffn.0, ffn.2; then the head's ffn.0; then per layer the K|V rows and the Q rows
 // of in_proj (index 4*n_layers + 1 + 2*i, + 1)
@@ -27,3 +27,9 @@ int tc_ntile(int N);
 int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab);
 int launch_linear_tc(const LinArgs& a, int epi, int G, const uint8_t* const* packed, long long pk_off, cudaStream_t st,
                      const TcEmbed* emb = nullptr);
+
+// fused acting forward (act_fused.cu): context ring -> (x2[last], final-layer attention row) per sequence, one launch
+bool act_fused_supported(const dtqn_net_cfg& c, int L);
+int launch_act_fused(const dtqn_net_cfg& c, const NetLayout& lay, const GroupPtrs& P, const GroupSrc& S, int G,
+                     const uint8_t* const* packed, long long img_off, int n_seq, int L, float* xl, float* ol, cudaStream_t st);
+int act_fused_tc_error();

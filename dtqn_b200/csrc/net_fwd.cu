@@ -632,7 +632,10 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         if (epi == EPI_BIAS_RELU) return launch_linear<EPI_BIAS_RELU>(a, G, d, st);
         return launch_linear<EPI_RES_LN>(a, G, d, st);
     };
-    if (!fuse_embed) {
+    // acting forward of the default 2-layer / d_model 64 network: ONE tcgen05 kernel from the context ring to the final
+    // layer's (residual row, attention row) per sequence -- no embedding, q|k|v, attention or FFN activations in HBM
+    const bool act_fused = use_tc && q_mode == 1 && !save && tab.act_img_off >= 0 && act_fused_supported(*cfg, L);
+    if (!fuse_embed && !act_fused) {
         prof_begin(PROF_EMBED, st);
         if (!cfg->discrete && cfg->obs_dim <= 16) {
             if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
@@ -651,7 +654,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     // acting (q_mode 1) needs the final layer's output at ONE position per sequence: that layer only projects K/V for
     // every token; its query, attention row, out_proj, FFN and LayerNorms run on n_seq rows (exactly the same values).
     const bool last_only = q_mode == 1 && L >= 3 && H * 32 <= 256;
-    const int n_full = last_only ? cfg->n_layers - 1 : cfg->n_layers;
+    const int n_full = act_fused ? 0 : (last_only ? cfg->n_layers - 1 : cfg->n_layers);
     for (int li = 0; li < n_full; ++li) {
         const LayerOff& lo = lay.layer[li];
         const LayerAct& la = act.layer[li];
@@ -726,6 +729,11 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         const long long nd = (long long)G * n_seq * d;
         float* xl = la.h;                 // [G*n_seq, d] carved out of the (T x 4d) FFN buffer: 9*n_seq*d <= n_seq*L*4d
         float* qlb = xl + nd; float* olb = qlb + nd; float* x1l = olb + nd; float* hl = x1l + nd; float* x2l = hl + 4 * nd;
+        LinArgs a{};
+        a.P = P;
+        if (act_fused) {
+            if ((rc = launch_act_fused(*cfg, lay, P, S, G, pk, tab.act_img_off, n_seq, L, xl, olb, st))) return rc;
+        } else {
         {
             dim3 grid(dtqn_cdiv((long long)n_seq * d, 256), 1, G);
             prof_begin(PROF_OTHER, st);
@@ -733,8 +741,6 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
             prof_end(PROF_OTHER, st, 0.0);
             DTQN_LAUNCH_CHECK();
         }
-        LinArgs a{};
-        a.P = P;
         // K | V of every token: rows [d, 3d) of in_proj
         a.Tg = (int)Tg; a.X = x_in; a.Y = la.qkv; a.w_off = lo.in_w + (long long)d * d; a.b_off = lo.in_b + d; a.N = 2 * d; a.K = d;
         if ((rc = linear(a, EPI_BIAS, 4 * cfg->n_layers + 1 + 2 * li))) return rc;
@@ -759,6 +765,8 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
             prof_end(PROF_ATTN_FWD, st, 4.0 * (double)G * n_seq * L * d);
             DTQN_LAUNCH_CHECK();
         }
+        }
+        a.Tg = n_seq;
         a.X = olb; a.Y = x1l; a.w_off = lo.out_w; a.b_off = lo.out_b; a.N = d; a.K = d;
         a.R = xl; a.gamma_off = lo.ln1_w; a.beta_off = lo.ln1_b; a.r_save = nullptr; a.st_save = nullptr;
         if ((rc = launch_linear<EPI_RES_LN>(a, G, d, st))) return rc;

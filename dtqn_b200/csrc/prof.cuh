@@ -21,7 +21,8 @@ enum ProfTag {
     PROF_OTHER = 13,
     PROF_LINEAR_TC = 14, // tcgen05 Linear launches; work = algorithmic BYTES (fp32 activations in + out, residual, weights)
     PROF_SEQ_FWD = 15,   // sequence-resident fused forward (all layers + head); work = FLOPs
-    PROF_NTAGS = 16
+    PROF_ACT_FUSED = 16, // fused acting forward (embed + layer 0 + final-layer K|V + last-row attention); work = FLOPs
+    PROF_NTAGS = 17
 };
 
 extern bool g_prof_on;

@@ -12,6 +12,7 @@ constexpr int TC_M = 128;                 // rows per tile = UMMA M
 constexpr int TC_KC = 64;                 // K elements per smem stage
 constexpr int A_CHUNK_STRIDE = TC_M * 16 + 16;   // bytes between 8-element k-chunks of the A tile (+16: conflict-free stores)
 constexpr int A_HALF_BYTES = (TC_KC / 8) * A_CHUNK_STRIDE;   // one of hi / lo
+constexpr int A_STAGE_BYTES = (2 * A_HALF_BYTES + 1023) & ~1023;   // one [128 x 64] hi + lo operand stage
 
 __device__ int g_tc_error = 0;
 

@@ -203,6 +203,11 @@ int dtqn_set_tc_fuse_ffn(int32_t on);
 /* 1 (default): the attention core of d_model 64 / 8 heads / L <= 64 groups outside the sequence-resident kernel (the acting
  * forward) runs on the warp-level tensor cores (mma.sync TF32 hi/lo split); 0: fp32 CUDA-core kernel. */
 int dtqn_set_attn_mma(int32_t on);
+/* 1 (default): the acting forward (q_mode 1) of the default architecture (2 layers, d_model 64, 8 heads, continuous
+ * observations, seq_len <= 52) with tcgen05 weight images runs embedding, the whole first layer, the final layer's in_proj
+ * and the attention row of the last valid position as ONE persistent tcgen05 kernel per 128-token tile (no activations
+ * in HBM); 0: one kernel per GEMM / attention. */
+int dtqn_set_act_fused(int32_t on);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 

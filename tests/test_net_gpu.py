@@ -320,3 +320,93 @@ def test_attention_mma_vs_oracle(golden_dir, L):
     print(f"L={L}: rel err mma {e_mma:.3e}  cuda-core {e_simt:.3e}")
     assert e_simt < Q_REL_TIGHT
     assert e_mma < Q_REL_TIGHT, e_mma
+
+
+def _acting_agent(golden_dir, K):
+    from dtqn_b200.agents import DtqnAgent
+    z = np.load(os.path.join(golden_dir, "acting_carflag.npz"))
+    d, layers, ctx, heads = [int(v) for v in z["meta"]]
+    agent = DtqnAgent(lambda: _make_net(z, "policy/", "carflag"), 200 * K * 2, "cuda", 3, 200, -5, 3, False, context_len=ctx, n_envs=K)
+    return agent, {k: v.float() for k, v in _sd(z, "policy/").items()}, ctx
+
+
+@pytest.mark.parametrize("K", [1, 2, 301, 1024])
+def test_acting_fused_kernel_vs_oracle(golden_dir, K):
+    """The fused acting kernel (embed + layer 0 + final-layer in_proj + last-row attention in one tcgen05 launch) against the
+    fp32 CPU oracle on windows of every length (1 .. ctx, wrapped rings, odd sequence counts -> half-empty last tile) and
+    against the kernel-per-GEMM tcgen05 path on the same contexts."""
+    from dtqn_b200 import networks, _lib
+    from oracle import network as onet
+    agent, sd, ctx = _acting_agent(golden_dir, K)
+    g = torch.Generator().manual_seed(11 + K)
+    ring = torch.trunc(torch.empty(K, ctx, 3).uniform_(-1.5, 1.5, generator=g))
+    ring[:, :, 0] = torch.empty(K, ctx).uniform_(-1.2, 1.2, generator=g)          # also non-integer rows (trunc_obs = 0 contexts)
+    ts = torch.randint(0, 180, (K,), generator=g).int()
+    ts[: min(K, ctx + 2)] = torch.arange(min(K, ctx + 2)).int()                     # every window length 1 .. ctx (+ wrapped)
+    agent.context.obs.copy_(ring); agent.context.timestep_t.copy_(ts)
+    ref = np.zeros((K, 3), np.float32)
+    for n in range(1, ctx + 1):
+        idx = [i for i in range(K) if min(ctx, int(ts[i]) + 1) == n]
+        if not idx:
+            continue
+        win = torch.stack([torch.stack([ring[i, (int(ts[i]) + 1 - n + j) % ctx] for j in range(n)]) for i in idx])
+        with torch.no_grad():
+            ref[idx] = onet.forward(sd, win, 8)[:, -1].numpy()
+    networks.set_tc_min_tokens(1)
+    try:
+        _lib.lib.dtqn_set_act_fused(1)
+        q_fused = agent.q_last_batched().cpu().numpy()
+        torch.cuda.synchronize()
+        assert not networks.tc_error(), "a tcgen05 kernel timed out on an mbarrier"
+        _lib.lib.dtqn_set_act_fused(0)
+        q_plain = agent.q_last_batched().cpu().numpy()
+    finally:
+        _lib.lib.dtqn_set_act_fused(1)
+        networks.set_tc_min_tokens(4096)
+    e_f, e_p = rel_err(q_fused, ref), rel_err(q_plain, ref)
+    print(f"K={K}: rel err fused {e_f:.3e}  kernel-per-GEMM tcgen05 {e_p:.3e}")
+    assert np.isfinite(q_fused).all()
+    assert e_p < 2e-4
+    assert e_f < Q_REL_TOL and e_f < 2e-4, e_f
+    scale = np.abs(ref).max()
+    worst = np.abs(q_fused - ref).max(axis=1) / scale
+    assert worst.max() < 2e-4, int(worst.argmax())
+
+
+def test_acting_fused_kernel_peaked_softmax(golden_dir):
+    """Same comparison with the in_proj weights scaled up (peaked softmax, large scores) and non-trivial LayerNorm / bias
+    parameters, 4096 contexts (the bench shape: 2048 tiles over 148 persistent CTAs)."""
+    from dtqn_b200 import networks, _lib
+    from oracle import network as onet
+    K = 4096
+    agent, sd, ctx = _acting_agent(golden_dir, K)
+    g = torch.Generator().manual_seed(5)
+    for k, v in sd.items():
+        if k.endswith("attn_mask"):
+            continue
+        if k.endswith("in_proj_weight"):
+            v.mul_(12.0)
+        elif k.endswith("bias") or "position_encoding" in k:
+            v.add_(torch.empty_like(v).normal_(0, 0.05, generator=g))
+        elif "layernorm" in k:
+            v.add_(torch.empty_like(v).normal_(0, 0.1, generator=g))
+        else:
+            v.mul_(2.0)
+    agent.policy_network.load_state_dict(sd)
+    ring = torch.trunc(torch.empty(K, ctx, 3).uniform_(-1.5, 1.5, generator=g))
+    ts = torch.randint(0, 400, (K,), generator=g).int()
+    agent.context.obs.copy_(ring); agent.context.timestep_t.copy_(ts)
+    sub = list(range(0, K, 37)) + [K - 1]
+    ref = np.zeros((len(sub), 3), np.float32)
+    for r, i in enumerate(sub):
+        n = min(ctx, int(ts[i]) + 1)
+        win = torch.stack([ring[i, (int(ts[i]) + 1 - n + j) % ctx] for j in range(n)])[None]
+        with torch.no_grad():
+            ref[r] = onet.forward(sd, win, 8)[0, -1].numpy()
+    _lib.lib.dtqn_set_act_fused(1)
+    q = agent.q_last_batched().cpu().numpy()
+    torch.cuda.synchronize()
+    assert not networks.tc_error()
+    e = rel_err(q[sub], ref)
+    print(f"peaked softmax, 4096 contexts: rel err fused {e:.3e}")
+    assert np.isfinite(q).all() and e < 2e-4, e
