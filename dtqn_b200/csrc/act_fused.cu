@@ -17,7 +17,7 @@
 //               attention (warp = (sequence, head)), bf16 hi/lo split into the K-major A operand
 //   warp 16     lane 0 issues every tcgen05.mma (M = 128, N = 64, bf16 hi/lo split: 3 MMAs per k-step) + commits
 //   warp 17     lane 0 streams the weight image (15 chunks of 16 KB per tile: [64 x 64] hi + lo, consumption order)
-//               through a 3-slot ring with cp.async.bulk (TMA) + mbarrier complete_tx
+//               through a 4-slot ring with cp.async.bulk (TMA) + mbarrier complete_tx
 // TMEM (512 columns): [0,256) in_proj / ffn.0 / layer-1 in_proj accumulators, [256,320) out_proj, [320,384) ffn.2.
 #include "net.cuh"
 #include "prof.cuh"
@@ -30,23 +30,26 @@ namespace {
 constexpr int AF_WORKERS = 512;
 constexpr int AF_THREADS = AF_WORKERS + 64;
 constexpr int AF_NCHUNK = 15;                     // weight chunks per tile
-constexpr int AF_WSLOTS = 3;
+constexpr int AF_WSLOTS = 4;
 constexpr uint32_t AF_WCHUNK = 64 * TC_KC * 4;    // [64 x 64] hi + lo
 constexpr int AF_QKV_ROWS = 116;                  // rows of the staged q|k|v tile (L + 64 <= 116)
-constexpr int AF_XLD = 68;                        // fp32 residual tile row stride (floats): conflict-free float4 per row
 constexpr int AF_MAX_L = 52;
+// A operand tile [128 x 64] bf16, K-major SWIZZLE_NONE: 8-element k-chunks AF_CS bytes apart, UNPADDED so every 8 x 16 B core
+// matrix is one aligned 128-byte line for the tensor core's operand fetch (a warp writes 32 consecutive rows of one chunk =
+// 512 contiguous bytes, so the stores are conflict-free without padding)
+constexpr int AF_CS = TC_M * 16, AF_AHALF = (TC_KC / 8) * AF_CS, AF_ASTAGE = 2 * AF_AHALF;
 constexpr uint32_t AF_R_BYTES = AF_QKV_ROWS * ATT_LD * 4;      // q|k|v tile; the 2-stage hidden-operand ring aliases it
-static_assert(AF_R_BYTES >= 2 * A_STAGE_BYTES, "hidden operand ring must fit in the qkv region");
+static_assert(AF_R_BYTES >= 2 * AF_ASTAGE, "hidden operand ring must fit in the qkv region");
 
 // parameter vectors staged in shared memory (float offsets)
 enum { P_INB0 = 0, P_OUTB0 = 192, P_LN1W = 256, P_LN1B = 320, P_F1B = 384, P_F2B = 640, P_LN2W = 704, P_LN2B = 768,
-       P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_TOTAL = 1344 };
+       P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_POS = 1344 /* [L][64] position table */, P_TOTAL = 1344 + AF_MAX_L * 64 };
 
-enum { B_W_FULL = 0, B_W_EMPTY = 3, B_AX0 = 6, B_AO = 7, B_AX1 = 8, B_AX2 = 9, B_ACC_QKV = 10, B_ACC_OUT = 11,
-       B_ACC1 = 12 /* +c */, B_ACC_F2 = 16, B_ACC_L1 = 17, B_A2_FULL = 18 /* +s */, B_A2_EMPTY = 20 /* +s */, B_COUNT = 22 };
+enum { B_W_FULL = 0, B_W_EMPTY = AF_WSLOTS, B_AX0 = 2 * AF_WSLOTS, B_AO, B_AX1, B_AX2, B_ACC_QKV, B_ACC_OUT, B_ACC_F2, B_ACC_L1,
+       B_ACC1 /* +c */, B_A2_FULL = B_ACC1 + 4 /* +s */, B_A2_EMPTY = B_A2_FULL + 2 /* +s */, B_COUNT = B_A2_EMPTY + 2 };
 
-constexpr size_t AF_SMEM = 1024 + AF_WSLOTS * AF_WCHUNK + A_STAGE_BYTES + AF_R_BYTES +
-                           128 * AF_XLD * 4 + P_TOTAL * 4 + 2 * 128 * 4 * 4 + 2 * 128 * 4 * 4 + 16 + 256 + B_COUNT * 8 + 16;
+constexpr size_t AF_SMEM = 1024 + AF_WSLOTS * AF_WCHUNK + AF_ASTAGE + AF_R_BYTES +
+                           P_TOTAL * 4 + 2 * 4 * 128 * 8 + 2 * 128 * 4 * 4 + 16 + 256 + B_COUNT * 8 + 16;
 static_assert(AF_SMEM <= 227 * 1024, "fused acting forward: shared memory budget");
 
 struct ActFusedArgs {
@@ -61,6 +64,9 @@ struct ActFusedArgs {
     float* ol;                                     // [G * n_seq, 64]  final-layer attention output of that position
 };
 
+// optional phase timeline (tools/prof_act.py --timeline): clock64 stamps of worker thread 0 of CTA 0, 32 per tile
+__device__ long long* g_af_dbg = nullptr;
+
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(AF_WORKERS) : "memory"); }
 
 __device__ __forceinline__ float warp_max_f(float v) {
@@ -74,14 +80,16 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// 12 MMAs: D[128 x 64] (+)= A[128 x 64] W[64 x 64]^T with the bf16 hi/lo split (hi*hi + hi*lo + lo*hi)
-__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint32_t a_u, uint32_t b_u, uint32_t idesc, bool acc_first) {
+// 12 MMAs: D[128 x 64] (+)= A[128 x 64] W[64 x 64]^T with the bf16 hi/lo split (hi*hi + hi*lo + lo*hi).  The operand
+// descriptors are built once per kernel (the single issuing thread is the pacing resource of every MMA phase); an smem
+// address offset is added to the start-address field, which never carries out of its 14 bits.
+struct ChunkDesc { uint64_t a_hi, a_lo; };
+__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, const ChunkDesc& a0, uint64_t b_hi0, uint32_t idesc, bool acc_first) {
+    constexpr uint64_t A_K16 = (2 * AF_CS) >> 4, B_K16 = (2 * 64 * 16) >> 4, B_LO = (AF_WCHUNK / 2) >> 4;
 #pragma unroll
     for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
-        const uint64_t a_hi = umma_desc(a_u + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
-        const uint64_t a_lo = umma_desc(a_u + A_HALF_BYTES + k16 * 2 * A_CHUNK_STRIDE, A_CHUNK_STRIDE, 128);
-        const uint64_t b_hi = umma_desc(b_u + k16 * 2 * (64 * 16), 64 * 16, 128);
-        const uint64_t b_lo = umma_desc(b_u + AF_WCHUNK / 2 + k16 * 2 * (64 * 16), 64 * 16, 128);
+        const uint64_t a_hi = a0.a_hi + k16 * A_K16, a_lo = a0.a_lo + k16 * A_K16;
+        const uint64_t b_hi = b_hi0 + k16 * B_K16, b_lo = b_hi + B_LO;
         umma_bf16(d_tmem, a_hi, b_hi, idesc, (acc_first || k16) ? 1u : 0u);
         umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
         umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
@@ -95,17 +103,15 @@ act_fused_kernel(ActFusedArgs t) {
     const int g = blockIdx.y;
     const int L = t.L;
 
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sW = base;                                            // weight ring
     uint8_t* sA = sW + AF_WSLOTS * AF_WCHUNK;                      // A operand (K = 64): x0 -> o -> x1 -> x2
-    uint8_t* sR = sA + A_STAGE_BYTES;
+    uint8_t* sR = sA + AF_ASTAGE;
     float* sQKV = reinterpret_cast<float*>(sR);                    // [AF_QKV_ROWS][ATT_LD]
     uint8_t* sA2 = sR;                                             // hidden operand ring (2 stages), aliases sQKV
-    float* sX = reinterpret_cast<float*>(sR + AF_R_BYTES);         // [128][AF_XLD] fp32 residual (x0, then x1)
-    float* sPar = sX + 128 * AF_XLD;
-    float* sRedA = sPar + P_TOTAL;                                 // [128][4] LayerNorm partial sums
-    float* sRedB = sRedA + 128 * 4;
-    float* sObs = sRedB + 128 * 4;                                 // [2][128][4] observation rows of the tile (double buffered)
+    float* sPar = reinterpret_cast<float*>(sR + AF_R_BYTES);
+    float* sRedA = sPar + P_TOTAL;                                 // [2][4][128] float2 LayerNorm partials (mean, M2)
+    float* sObs = sRedA + 2 * 4 * 128 * 2;                                // [2][128][4] observation rows of the tile (double buffered)
     int* sMeta = reinterpret_cast<int*>(sObs + 2 * 128 * 4);       // [2][2] valid length of the tile's two sequences
     uint8_t* sFlag = reinterpret_cast<uint8_t*>(sMeta + 4);        // [2][128] 1 = row belongs to a real sequence
     uint64_t* bars = reinterpret_cast<uint64_t*>(sFlag + 256);
@@ -132,7 +138,8 @@ act_fused_kernel(ActFusedArgs t) {
         else if (e < P_INB1) v = __ldg(p + t.l0.ln2_b + (e - P_LN2B));
         else if (e < P_EW) v = __ldg(p + t.l1.in_b + (e - P_INB1));
         else if (e < P_EB) { const int c = (e - P_EW) >> 2, k = (e - P_EW) & 3; v = k < t.O ? __ldg(p + t.emb_w + c * t.O + k) : 0.f; }
-        else v = __ldg(p + t.emb_b + (e - P_EB));
+        else if (e < P_POS) v = __ldg(p + t.emb_b + (e - P_EB));
+        else v = (e - P_POS) < L * 64 ? __ldg(p + t.pos + (e - P_POS)) : 0.f;
         sPar[e] = v;
     }
     if (tid == 0) {
@@ -207,9 +214,9 @@ act_fused_kernel(ActFusedArgs t) {
                 for (int e = 0; e < 8; ++e) x8[e] = y[hlf * 8 + e];
                 uint4 hi, lo;
                 split8(x8, hi, lo);
-                uint8_t* d = dstA + (cq * 2 + hlf) * A_CHUNK_STRIDE + row * 16;
+                uint8_t* d = dstA + (cq * 2 + hlf) * AF_CS + row * 16;
                 *reinterpret_cast<uint4*>(d) = hi;
-                *reinterpret_cast<uint4*>(d + A_HALF_BYTES) = lo;
+                *reinterpret_cast<uint4*>(d + AF_AHALF) = lo;
             }
         };
         // accumulator [128 x 192] (+ in_proj bias, q columns pre-scaled for the base-2 softmax) -> staged fp32 q|k|v tile
@@ -234,76 +241,93 @@ act_fused_kernel(ActFusedArgs t) {
                 }
             }
         };
-        // y = LayerNorm(x_res + relu(acc + b)) over the 64 columns of `row` (4 threads x 16 columns, reduced through smem);
-        // y replaces the residual tile row and becomes the next A operand
+        // y = LayerNorm(x + relu(acc + b)) over the 64 columns of `row` (4 threads x 16 columns, reduced through smem);
+        // the residual x lives in this thread's registers from the phase that produced it and is replaced by y
+        int ln_parity = 0;                                         // the two LayerNorms of a tile alternate reduction buffers
         auto res_ln = [&](uint32_t tm_col, int b_off, int gw_off, int gb_off, float (&y)[16]) {
             float v[16];
             tmem_ld16(tlane + tm_col + (uint32_t)c0, v);
             tc_fence_before();
-            float* xr = sX + row * AF_XLD + c0;
             float s = 0.f;
 #pragma unroll
             for (int q = 0; q < 16; q += 4) {
-                const float4 x4 = *reinterpret_cast<const float4*>(xr + q);
-                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                const float4 b4 = *reinterpret_cast<const float4*>(sPar + b_off + c0 + q);
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { y[q + e] = xv[e] + fmaxf(v[q + e] + sPar[b_off + c0 + q + e], 0.f); s += y[q + e]; }
+                for (int e = 0; e < 4; ++e) { y[q + e] += fmaxf(v[q + e] + bv[e], 0.f); s += y[q + e]; }
             }
-            sRedA[row * 4 + cq] = s;
-            worker_bar();
-            const float4 ra = *reinterpret_cast<const float4*>(sRedA + row * 4);
-            const float mean = ((ra.x + ra.y) + (ra.z + ra.w)) * (1.f / 64.f);
-            float vs = 0.f;
+            // mean / variance of the row from four 16-column partials (mean_i, M2_i), combined exactly (Chan et al.)
+            const float mi = s * (1.f / 16.f);
+            float m2 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { const float dl = y[e] - mean; vs = fmaf(dl, dl, vs); }
-            sRedB[row * 4 + cq] = vs;
+            for (int e = 0; e < 16; ++e) { const float dl = y[e] - mi; m2 = fmaf(dl, dl, m2); }
+            float2* red = reinterpret_cast<float2*>(sRedA) + (size_t)(ln_parity * 4) * 128;
+            red[cq * 128 + row] = make_float2(mi, m2);
             worker_bar();
-            const float4 rb = *reinterpret_cast<const float4*>(sRedB + row * 4);
-            const float rstd = 1.0f / sqrtf(((rb.x + rb.y) + (rb.z + rb.w)) * (1.f / 64.f) + 1e-5f);
+            const float2 r0 = red[row], r1 = red[128 + row], r2 = red[256 + row], r3 = red[384 + row];
+            const float mean = ((r0.x + r1.x) + (r2.x + r3.x)) * 0.25f;
+            const float d0 = r0.x - mean, d1 = r1.x - mean, d2 = r2.x - mean, d3 = r3.x - mean;
+            const float var = (((r0.y + r1.y) + (r2.y + r3.y)) + 16.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3))) * (1.f / 64.f);
+            const float rstd = 1.0f / sqrtf(var + 1e-5f);
+            ln_parity ^= 1;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) y[e] = (y[e] - mean) * rstd * sPar[gw_off + c0 + e] + sPar[gb_off + c0 + e];
+            for (int q = 0; q < 16; q += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(sPar + gw_off + c0 + q);
+                const float4 e4 = *reinterpret_cast<const float4*>(sPar + gb_off + c0 + q);
+                y[q] = (y[q] - mean) * rstd * g4.x + e4.x; y[q + 1] = (y[q + 1] - mean) * rstd * g4.y + e4.y;
+                y[q + 2] = (y[q + 2] - mean) * rstd * g4.z + e4.z; y[q + 3] = (y[q + 3] - mean) * rstd * g4.w + e4.w;
+            }
+        };
+
+        // token embedding of this thread's 16 columns of `row`: x0 = W_e obs + b_e + pos[j]  (rows outside a real sequence: 0)
+        auto embed_row = [&](int buf, float (&x)[16]) {
+            const float4 o4 = *reinterpret_cast<const float4*>(sObs + (buf * 128 + row) * 4);
+            const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
+            const bool real = sFlag[buf * 128 + row] != 0;
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (real) pv = *reinterpret_cast<const float4*>(sPar + P_POS + jrow * 64 + c0 + q);
+                const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+                const float4 b4 = *reinterpret_cast<const float4*>(sPar + P_EB + c0 + q);
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(sPar + P_EW + (c0 + q + e) * 4);
+                    float acc = bv[e];
+                    acc = fmaf(ov[0], w4.x, acc); acc = fmaf(ov[1], w4.y, acc); acc = fmaf(ov[2], w4.z, acc); acc = fmaf(ov[3], w4.w, acc);
+                    x[q + e] = real ? acc + pvv[e] : 0.f;
+                }
+            }
         };
 
         if (my_tiles > 0 && loader) { obs_ts((int)blockIdx.x); obs_rows((int)blockIdx.x); obs_store(0); }
         worker_bar();
 
+        long long* dbg = (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ? g_af_dbg : nullptr;
+        auto STAMP = [&](int i, int k) { if (dbg && i < 8) dbg[i * 32 + k] = clock64(); };
         for (int i = 0; i < my_tiles; ++i) {
+            STAMP(i, 0);
             const int tile = (int)blockIdx.x + i * (int)gridDim.x;
             const int tile_next = tile + (int)gridDim.x;
             const bool has_next = i + 1 < my_tiles;
             const uint32_t ph = (uint32_t)(i & 1);
             const int buf = i & 1;
 
-            // ---- token embedding: x0 = W_e obs + b_e + pos[j]  (rows outside a real sequence: 0) ----
-            {
-                const float4 o4 = *reinterpret_cast<const float4*>(sObs + (buf * 128 + row) * 4);
-                const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
-                const bool real = sFlag[buf * 128 + row] != 0;
-                float y[16];
-#pragma unroll
-                for (int q = 0; q < 16; q += 4) {
-                    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (real) pv = __ldg(reinterpret_cast<const float4*>(p + t.pos + (long long)jrow * 64 + c0 + q));
-                    const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float acc = sPar[P_EB + c0 + q + e];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc = fmaf(ov[k], sPar[P_EW + (c0 + q + e) * 4 + k], acc);
-                        y[q + e] = real ? acc + pvv[e] : 0.f;
-                    }
-                    *reinterpret_cast<float4*>(sX + row * AF_XLD + c0 + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
-                }
-                store_a(sA, y);
-                fence_async_smem();
-                mbar_arrive(BAR(B_AX0));
-            }
+            // ---- token embedding -> A operand ----
+            float xres[16];
+            embed_row(buf, xres);
+            store_a(sA, xres);
+            fence_async_smem();
+            mbar_arrive(BAR(B_AX0));
+            STAMP(i, 1);
             // ---- layer-0 q|k|v: TMEM -> shared memory ----
             WAIT(B_ACC_QKV, ph);
+            STAMP(i, 2);
             tc_fence_after();
             dump_qkv(P_INB0);
-            if (has_next && loader) obs_ts(tile_next);
             worker_bar();
+            STAMP(i, 3);
             // ---- causal attention, warp = (sequence, head); o -> A operand ----
             {
                 const int s = warp >> 3, h = warp & 7;
@@ -315,69 +339,77 @@ act_fused_kernel(ActFusedArgs t) {
                             const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
                             const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
                             const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-                            uint8_t* d = sA + (col >> 3) * A_CHUNK_STRIDE + (rbase + r) * 16 + (col & 7) * 2;
+                            uint8_t* d = sA + (col >> 3) * AF_CS + (rbase + r) * 16 + (col & 7) * 2;
                             *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(h0, h1);
-                            *reinterpret_cast<uint32_t*>(d + A_HALF_BYTES) = pack_bf16x2(l0, l1);
+                            *reinterpret_cast<uint32_t*>(d + AF_AHALF) = pack_bf16x2(l0, l1);
                         }
                     });
                 }
-                if (has_next && loader) obs_rows(tile_next);
+                STAMP(i, 4);
                 fence_async_smem();
                 mbar_arrive(BAR(B_AO));
+                // next tile's observation rows: the dependent timestep -> ring-row loads hide behind the out_proj wait
+                if (has_next && loader) { obs_ts(tile_next); obs_rows(tile_next); obs_store(buf ^ 1); }
             }
             // ---- out_proj -> ReLU -> +x0 -> LayerNorm1 -> x1 ----
             WAIT(B_ACC_OUT, ph);
+            STAMP(i, 5);
             tc_fence_after();
-            if (has_next && loader) obs_store(buf ^ 1);
-            {
-                float y[16];
-                res_ln(TM_OUT, P_OUTB0, P_LN1W, P_LN1B, y);
-#pragma unroll
-                for (int q = 0; q < 16; q += 4)
-                    *reinterpret_cast<float4*>(sX + row * AF_XLD + c0 + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
-                store_a(sA, y);
-                fence_async_smem();
-                mbar_arrive(BAR(B_AX1));
-            }
+            embed_row(buf, xres);                                  // residual x0 recomputed (cheaper than carrying 16 registers)
+            res_ln(TM_OUT, P_OUTB0, P_LN1W, P_LN1B, xres);        // xres: x0 -> x1
+            store_a(sA, xres);
+            fence_async_smem();
+            mbar_arrive(BAR(B_AX1));
+            STAMP(i, 6);
             // ---- ffn.0 accumulator chunk c -> +b1 -> ReLU -> hi/lo -> hidden operand ring ----
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int m = 2 * i + (c >> 1), s_ = c & 1;
                 WAIT(B_ACC1 + c, ph);
+                STAMP(i, 7 + 3 * c);
                 tc_fence_after();
                 float v[16];
                 tmem_ld16(tlane + (uint32_t)(c * 64 + c0), v);
                 tc_fence_before();
                 if (m >= 1) WAIT(B_A2_EMPTY + s_, (uint32_t)((m - 1) & 1));
+                STAMP(i, 8 + 3 * c);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e] + sPar[P_F1B + c * 64 + c0 + e], 0.f);
-                store_a(sA2 + s_ * A_STAGE_BYTES, v);
+                for (int q = 0; q < 16; q += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sPar + P_F1B + c * 64 + c0 + q);
+                    v[q] = fmaxf(v[q] + b4.x, 0.f); v[q + 1] = fmaxf(v[q + 1] + b4.y, 0.f);
+                    v[q + 2] = fmaxf(v[q + 2] + b4.z, 0.f); v[q + 3] = fmaxf(v[q + 3] + b4.w, 0.f);
+                }
+                store_a(sA2 + s_ * AF_ASTAGE, v);
                 fence_async_smem();
                 mbar_arrive(BAR(B_A2_FULL + s_));
+                STAMP(i, 9 + 3 * c);
             }
             // ---- ffn.2 -> ReLU -> +x1 -> LayerNorm2 -> x2 ----
             WAIT(B_ACC_F2, ph);
+            STAMP(i, 19);
             tc_fence_after();
             {
-                float y[16];
-                res_ln(TM_F2, P_F2B, P_LN2W, P_LN2B, y);
-                store_a(sA, y);
+                res_ln(TM_F2, P_F2B, P_LN2W, P_LN2B, xres);       // xres: x1 -> x2
+                store_a(sA, xres);
                 if (sl < 2) {
                     const int n = sMeta[buf * 2 + sl];
                     if (n > 0 && jrow == n - 1) {                  // residual of the final layer's LayerNorm1
                         float* dst = t.xl + ((long long)g * t.n_seq + tile * 2 + sl) * 64 + c0;
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                        for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(xres[q], xres[q + 1], xres[q + 2], xres[q + 3]);
                     }
                 }
                 fence_async_smem();
                 mbar_arrive(BAR(B_AX2));
             }
+            STAMP(i, 20);
             // ---- final layer: q|k|v -> shared memory, attention row of the last valid position ----
             WAIT(B_ACC_L1, ph);
+            STAMP(i, 21);
             tc_fence_after();
             dump_qkv(P_INB1);
             worker_bar();
+            STAMP(i, 22);
             {
                 const int s = warp >> 3, h = warp & 7;
                 const int n = sMeta[buf * 2 + s];
@@ -414,56 +446,97 @@ act_fused_kernel(ActFusedArgs t) {
                         }
                     }
                     l = warp_sum_f(l);
-                    float mine = 0.f;
+                    // 8 sums over 32 lanes by halving: after the three exchanges lane (b4 b3 b2 . .) holds column 4 b4 + 2 b3 + b2
+                    float a4[4], a2[2], a1;
+                    {
+                        const bool up = lane & 16;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float a = warp_sum_f(acc[c]);
-                        if (lane == c) mine = a;
+                        for (int c = 0; c < 4; ++c) {
+                            const float send = up ? acc[c] : acc[c + 4];
+                            a4[c] = (up ? acc[c + 4] : acc[c]) + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
                     }
-                    if (lane < 8) t.ol[((long long)g * t.n_seq + tile * 2 + s) * 64 + h * 8 + lane] = mine / l;
+                    {
+                        const bool up = lane & 8;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const float send = up ? a4[c] : a4[c + 2];
+                            a2[c] = (up ? a4[c + 2] : a4[c]) + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                    }
+                    {
+                        const bool up = lane & 4;
+                        const float send = up ? a2[0] : a2[1];
+                        a1 = (up ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    if ((lane & 3) == 0) {
+                        const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        t.ol[((long long)g * t.n_seq + tile * 2 + s) * 64 + h * 8 + c] = a1 / l;
+                    }
                 }
             }
+            STAMP(i, 23);
         }
     } else if (warp == 16) {
         // =============================================== MMA issuer ===============================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(TC_M, 64);
-            const uint32_t sA_u = smem_u32(sA), sA2_u = smem_u32(sA2), sW_u = smem_u32(sW);
-            int n = 0;                                             // running weight-chunk counter (ring position)
-            auto wslot = [&]() -> uint32_t {                       // wait for chunk n, return its smem address
-                WAIT(B_W_FULL + n % AF_WSLOTS, (uint32_t)((n / AF_WSLOTS) & 1));
-                return sW_u + (uint32_t)(n % AF_WSLOTS) * AF_WCHUNK;
+            const ChunkDesc dA{umma_desc(smem_u32(sA), AF_CS, 128), umma_desc(smem_u32(sA) + AF_AHALF, AF_CS, 128)};
+            const ChunkDesc dA2[2] = {
+                {umma_desc(smem_u32(sA2), AF_CS, 128), umma_desc(smem_u32(sA2) + AF_AHALF, AF_CS, 128)},
+                {umma_desc(smem_u32(sA2) + AF_ASTAGE, AF_CS, 128), umma_desc(smem_u32(sA2) + AF_ASTAGE + AF_AHALF, AF_CS, 128)}};
+            const uint64_t dW0 = umma_desc(smem_u32(sW), 64 * 16, 128);
+            int n = 0, slot = 0;                                   // running weight-chunk counter and its ring slot
+            uint32_t wpar = 0;                                     // parity of the current pass over the ring
+            auto wslot = [&]() -> uint64_t {                       // wait for chunk n, return its B descriptor (hi half)
+                WAIT(B_W_FULL + slot, wpar);
+                return dW0 + (uint64_t)slot * (AF_WCHUNK >> 4);
             };
-            auto wdone = [&]() { umma_commit(BAR(B_W_EMPTY + n % AF_WSLOTS)); ++n; };
+            auto wdone = [&]() {
+                umma_commit(BAR(B_W_EMPTY + slot));
+                ++n; if (++slot == AF_WSLOTS) { slot = 0; wpar ^= 1u; }
+            };
+            long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? g_af_dbg : nullptr;
+            auto STAMP = [&](int i, int k) { if (dbg && i < 8) dbg[i * 32 + k] = clock64(); };
             for (int i = 0; i < my_tiles; ++i) {
                 const uint32_t ph = (uint32_t)(i & 1);
                 WAIT(B_AX0, ph);
+                STAMP(i, 24);
                 tc_fence_after();
-                for (int c = 0; c < 3; ++c) { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone(); }
+                for (int c = 0; c < 3; ++c) { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone(); }
                 umma_commit(BAR(B_ACC_QKV));
+                STAMP(i, 25);
                 WAIT(B_AO, ph);
+                STAMP(i, 26);
                 tc_fence_after();
-                { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + TM_OUT, sA_u, b, idesc, false); wdone(); }
+                { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + TM_OUT, dA, b, idesc, false); wdone(); }
                 umma_commit(BAR(B_ACC_OUT));
+                STAMP(i, 27);
                 WAIT(B_AX1, ph);
+                STAMP(i, 28);
                 tc_fence_after();
                 for (int c = 0; c < 4; ++c) {
-                    const uint32_t b = wslot(); tc_fence_after();
-                    mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone();
+                    const uint64_t b = wslot(); tc_fence_after();
+                    mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone();
                     umma_commit(BAR(B_ACC1 + c));
                 }
                 for (int c = 0; c < 4; ++c) {
                     const int m = 2 * i + (c >> 1), s_ = c & 1;
                     WAIT(B_A2_FULL + s_, (uint32_t)(m & 1));
-                    const uint32_t b = wslot(); tc_fence_after();
-                    mma_chunk(tmem + TM_F2, sA2_u + (uint32_t)s_ * A_STAGE_BYTES, b, idesc, c > 0); wdone();
+                    const uint64_t b = wslot(); tc_fence_after();
+                    mma_chunk(tmem + TM_F2, dA2[s_], b, idesc, c > 0); wdone();
                     umma_commit(BAR(B_A2_EMPTY + s_));
                 }
                 umma_commit(BAR(B_ACC_F2));
+                STAMP(i, 29);
                 WAIT(B_AX2, ph);
+                STAMP(i, 30);
                 tc_fence_after();
-                for (int c = 0; c < 3; ++c) { const uint32_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), sA_u, b, idesc, false); wdone(); }
+                for (int c = 0; c < 3; ++c) { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone(); }
                 umma_commit(BAR(B_ACC_L1));
+                STAMP(i, 31);
             }
         }
     } else {
@@ -519,6 +592,12 @@ int launch_act_fused(const dtqn_net_cfg& c, const NetLayout& lay, const GroupPtr
     prof_end(PROF_ACT_FUSED, st, flops);
     DTQN_LAUNCH_CHECK();
     return 0;
+}
+
+// debug: device buffer of >= 256 int64 receiving the phase timeline of CTA 0 (NULL: off)
+extern "C" int dtqn_set_act_fused_timeline(void* buf) {
+    long long* p = (long long*)buf;
+    return (int)cudaMemcpyToSymbol(g_af_dbg, &p, sizeof(p));
 }
 
 int act_fused_tc_error() {

@@ -92,7 +92,7 @@ linear_tc_kernel(TcArgs t) {
     constexpr int TMEM_COLS = N_TILE <= 64 ? 64 : (N_TILE <= 128 ? 128 : 256);
     constexpr uint32_t B_HALF = N_TILE * TC_KC * 2;               // bytes of one of hi / lo of a weight block
 
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = base;                                            // hi then lo, A_HALF_BYTES each
     uint8_t* sB = base + ((2 * A_HALF_BYTES + 1023) & ~1023);      // hi then lo, B_HALF each
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * B_HALF); // [0] weights landed, [1] MMAs retired
@@ -312,7 +312,7 @@ linear_tc_pipe_kernel(TcArgs t) {
     constexpr uint32_t B_HALF = N_TILE * TC_KC * 2;            // one of hi / lo of one k-chunk block
     constexpr uint32_t B_BYTES = 2 * B_HALF * K_CHUNKS;
 
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sB = base;                                        // resident weight image: K_CHUNKS x {hi, lo}
     uint8_t* sA = sB + ((B_BYTES + 1023) & ~1023u);            // 2 stages
     uint8_t* sStg = sA + 2 * A_STAGE_BYTES;                    // 2 staging buffers
@@ -642,7 +642,7 @@ ffn_tc_kernel(FfnArgs t) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
 
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sW1 = base;
     uint8_t* sW2 = sW1 + W1_BYTES;                             // 2 stages
     uint8_t* sA1 = sW2 + 2 * W2C_BYTES;

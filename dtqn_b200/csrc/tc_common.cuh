@@ -90,16 +90,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 8 floats -> two 16-byte chunks
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values at a time: one packed convert (F2FP.BF16.PACK_AB) per
+// half, the hi halves widened back to fp32 with a shift / mask
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // .x = a -> bits [0,16), .y = b -> bits [16,32)
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 8 floats -> two 16-byte chunks
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __float2bfloat16_rn(x[i]);
-        l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
-    }
-    hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    split2(x[0], x[1], hi.x, lo.x);
+    split2(x[2], x[3], hi.y, lo.y);
+    split2(x[4], x[5], hi.z, lo.z);
+    split2(x[6], x[7], hi.w, lo.w);
 }
 
 

@@ -208,6 +208,8 @@ int dtqn_set_attn_mma(int32_t on);
  * and the attention row of the last valid position as ONE persistent tcgen05 kernel per 128-token tile (no activations
  * in HBM); 0: one kernel per GEMM / attention. */
 int dtqn_set_act_fused(int32_t on);
+/* debug: device buffer of >= 256 int64 that receives clock64 phase stamps of CTA 0 of the fused acting kernel (NULL: off). */
+int dtqn_set_act_fused_timeline(void* device_buf);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
 int dtqn_tc_error(void);
 
