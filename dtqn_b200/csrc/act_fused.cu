@@ -15,10 +15,11 @@
 // Roles (576 threads, 1 CTA / SM, persistent over tiles):
 //   warps 0-15  workers: embed, TMEM epilogues (thread = row, 16 columns each; LayerNorm reduced through smem),
 //               attention (warp = (sequence, head)), bf16 hi/lo split into the K-major A operand
-//   warp 16     lane 0 issues every tcgen05.mma (M = 128, N = 64, bf16 hi/lo split: 3 MMAs per k-step) + commits
-//   warp 17     lane 0 streams the weight image (15 chunks of 16 KB per tile: [64 x 64] hi + lo, consumption order)
-//               through a 4-slot ring with cp.async.bulk (TMA) + mbarrier complete_tx
-// TMEM (512 columns): [0,256) in_proj / ffn.0 / layer-1 in_proj accumulators, [256,320) out_proj, [320,384) ffn.2.
+//   warp 16     lane 0 issues every tcgen05.mma (M = 128, N = 192 / 128 / 64 -- wide N amortises the A-operand fetch from
+//               shared memory, which paces these K = 64 GEMMs; bf16 hi/lo split: 3 MMAs per k-step) + commits
+//   warp 17     lane 0 streams the weight image (240 KB per tile, L2-resident) through a 64 KB shared-memory buffer with
+//               cp.async.bulk (TMA) + mbarrier complete_tx, each block as soon as the MMAs reading its slots have retired
+// TMEM (512 columns): [0,256) in_proj / ffn.0 accumulators (+ x0 stash), [256,320) out_proj / ffn.2, [320,512) final-layer in_proj.
 #include "net.cuh"
 #include "prof.cuh"
 #include "linear_tc.cuh"
@@ -29,9 +30,11 @@ namespace {
 
 constexpr int AF_WORKERS = 512;
 constexpr int AF_THREADS = AF_WORKERS + 64;
-constexpr int AF_NCHUNK = 15;                     // weight chunks per tile
-constexpr int AF_WSLOTS = 4;
-constexpr uint32_t AF_WCHUNK = 64 * TC_KC * 4;    // [64 x 64] hi + lo
+constexpr uint32_t AF_WCHUNK = 64 * TC_KC * 4;    // [64 x 64] hi + lo = one 16 KB slot of the weight buffer
+constexpr uint32_t AF_WBYTES = 4 * AF_WCHUNK;     // weight buffer: 4 slots
+// weight image (tc_pack_table): in_proj0 [192 x 64] | out_proj0 [64 x 64] | ffn.0 as two [128 x 64] halves | ffn.2 as four
+// [64 x 64] k-chunks | in_proj1 [192 x 64]; every block = { hi[8 k-chunks][N][8 bf16], lo[...] }
+constexpr uint32_t IMG_IN0 = 0, IMG_OUT = 3 * AF_WCHUNK, IMG_F1 = 4 * AF_WCHUNK, IMG_F2 = 8 * AF_WCHUNK, IMG_IN1 = 12 * AF_WCHUNK;
 constexpr int AF_QKV_ROWS = 116;                  // rows of the staged q|k|v tile (L + 64 <= 116)
 constexpr int AF_MAX_L = 52;
 // A operand tile [128 x 64] bf16, K-major SWIZZLE_NONE: 8-element k-chunks AF_CS bytes apart, UNPADDED so every 8 x 16 B core
@@ -45,10 +48,12 @@ static_assert(AF_R_BYTES >= 2 * AF_ASTAGE, "hidden operand ring must fit in the 
 enum { P_INB0 = 0, P_OUTB0 = 192, P_LN1W = 256, P_LN1B = 320, P_F1B = 384, P_F2B = 640, P_LN2W = 704, P_LN2B = 768,
        P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_POS = 1344 /* [L][64] position table */, P_TOTAL = 1344 + AF_MAX_L * 64 };
 
-enum { B_W_FULL = 0, B_W_EMPTY = AF_WSLOTS, B_AX0 = 2 * AF_WSLOTS, B_AO, B_AX1, B_AX2, B_ACC_QKV, B_ACC_OUT, B_ACC_F2, B_ACC_L1,
-       B_ACC1 /* +c */, B_A2_FULL = B_ACC1 + 4 /* +s */, B_A2_EMPTY = B_A2_FULL + 2 /* +s */, B_COUNT = B_A2_EMPTY + 2 };
+// weight buffer hand-offs (each barrier completes once per tile): F_* "landed" (TMA complete_tx), E_* "consumed" (tcgen05.commit)
+enum { F_IN0 = 0, F_OUT, F_F1A, F_F1B, F_F2 /* +k */, F_IN1 = F_F2 + 4, E_IN0, E_OUT, E_F1A, E_F1B, E_F2K2, E_F2K3, E_IN1,
+       B_AX0, B_AO, B_AX1, B_AX2, B_ACC_QKV, B_ACC_OUT, B_ACC_F2, B_ACC_L1, B_ACC1 /* +half */,
+       B_A2_FULL = B_ACC1 + 2 /* +s */, B_A2_EMPTY = B_A2_FULL + 2 /* +s */, B_COUNT = B_A2_EMPTY + 2 };
 
-constexpr size_t AF_SMEM = 1024 + AF_WSLOTS * AF_WCHUNK + AF_ASTAGE + AF_R_BYTES +
+constexpr size_t AF_SMEM = 1024 + AF_WBYTES + AF_ASTAGE + AF_R_BYTES +
                            P_TOTAL * 4 + 2 * 4 * 128 * 8 + 2 * 128 * 4 * 4 + 16 + 256 + B_COUNT * 8 + 16;
 static_assert(AF_SMEM <= 227 * 1024, "fused acting forward: shared memory budget");
 
@@ -84,8 +89,11 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // descriptors are built once per kernel (the single issuing thread is the pacing resource of every MMA phase); an smem
 // address offset is added to the start-address field, which never carries out of its 14 bits.
 struct ChunkDesc { uint64_t a_hi, a_lo; };
-__device__ __forceinline__ void mma_chunk(uint32_t d_tmem, const ChunkDesc& a0, uint64_t b_hi0, uint32_t idesc, bool acc_first) {
-    constexpr uint64_t A_K16 = (2 * AF_CS) >> 4, B_K16 = (2 * 64 * 16) >> 4, B_LO = (AF_WCHUNK / 2) >> 4;
+// N = rows of the weight block (its k-chunks are N * 16 bytes apart, its lo half N * 128 bytes after the hi half)
+template <int N>
+__device__ __forceinline__ void mma_block(uint32_t d_tmem, const ChunkDesc& a0, uint64_t b_hi0, bool acc_first) {
+    constexpr uint64_t A_K16 = (2 * AF_CS) >> 4, B_K16 = (2 * N * 16) >> 4, B_LO = (N * TC_KC * 2) >> 4;
+    const uint32_t idesc = umma_idesc(TC_M, N);
 #pragma unroll
     for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
         const uint64_t a_hi = a0.a_hi + k16 * A_K16, a_lo = a0.a_lo + k16 * A_K16;
@@ -105,7 +113,7 @@ act_fused_kernel(ActFusedArgs t) {
 
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sW = base;                                            // weight ring
-    uint8_t* sA = sW + AF_WSLOTS * AF_WCHUNK;                      // A operand (K = 64): x0 -> o -> x1 -> x2
+    uint8_t* sA = sW + AF_WBYTES;                      // A operand (K = 64): x0 -> o -> x1 -> x2
     uint8_t* sR = sA + AF_ASTAGE;
     float* sQKV = reinterpret_cast<float*>(sR);                    // [AF_QKV_ROWS][ATT_LD]
     uint8_t* sA2 = sR;                                             // hidden operand ring (2 stages), aliases sQKV
@@ -143,11 +151,11 @@ act_fused_kernel(ActFusedArgs t) {
         sPar[e] = v;
     }
     if (tid == 0) {
-        for (int s = 0; s < AF_WSLOTS; ++s) { mbar_init(BAR(B_W_FULL + s), 1); mbar_init(BAR(B_W_EMPTY + s), 1); }
+        for (int b = F_IN0; b <= E_IN1; ++b) mbar_init(BAR(b), 1);
         mbar_init(BAR(B_AX0), AF_WORKERS); mbar_init(BAR(B_AO), AF_WORKERS);
         mbar_init(BAR(B_AX1), AF_WORKERS); mbar_init(BAR(B_AX2), AF_WORKERS);
         mbar_init(BAR(B_ACC_QKV), 1); mbar_init(BAR(B_ACC_OUT), 1); mbar_init(BAR(B_ACC_F2), 1); mbar_init(BAR(B_ACC_L1), 1);
-        for (int c = 0; c < 4; ++c) mbar_init(BAR(B_ACC1 + c), 1);
+        for (int c = 0; c < 2; ++c) mbar_init(BAR(B_ACC1 + c), 1);
         for (int s = 0; s < 2; ++s) { mbar_init(BAR(B_A2_FULL + s), AF_WORKERS); mbar_init(BAR(B_A2_EMPTY + s), 1); }
         *s_fail = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,7 +168,10 @@ act_fused_kernel(ActFusedArgs t) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    constexpr uint32_t TM_OUT = 256, TM_F2 = 320;
+    // TMEM columns: [0,192) layer-0 q|k|v, then [0,256) ffn.0 hidden; [192,256) doubles as the stash of the next x0 (residual
+    // of LayerNorm1) while free; [256,320) out_proj, then ffn.2; [320,512) final-layer q|k|v (so the NEXT tile's in_proj can
+    // run while this tile's last-row attention still reads it)
+    constexpr uint32_t TM_STASH = 192, TM_OUT = 256, TM_F2 = 256, TM_L1 = 320;
 
     const int tiles = (t.n_seq + 1) >> 1;
     const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -220,10 +231,10 @@ act_fused_kernel(ActFusedArgs t) {
             }
         };
         // accumulator [128 x 192] (+ in_proj bias, q columns pre-scaled for the base-2 softmax) -> staged fp32 q|k|v tile
-        auto dump_qkv = [&](int bias_off) {
+        auto dump_qkv = [&](int bias_off, uint32_t tm_base) {
             uint32_t r[3][16];
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) tmem_ld16_issue(tlane + (uint32_t)(cq * 48 + cc * 16), r[cc]);
+            for (int cc = 0; cc < 3; ++cc) tmem_ld16_issue(tlane + tm_base + (uint32_t)(cq * 48 + cc * 16), r[cc]);
             tmem_ld_wait();
             tc_fence_before();
             if (row < AF_QKV_ROWS) {
@@ -301,8 +312,21 @@ act_fused_kernel(ActFusedArgs t) {
             }
         };
 
+        // token embedding of a tile -> A operand of its in_proj; the fp32 row is parked in TMEM until LayerNorm1 needs it as residual
+        auto embed_publish = [&](int buf) {
+            float x0[16];
+            embed_row(buf, x0);
+            store_a(sA, x0);
+            tmem_st16(tlane + TM_STASH + (uint32_t)c0, x0);
+            tmem_st_wait();
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(B_AX0));
+        };
+
         if (my_tiles > 0 && loader) { obs_ts((int)blockIdx.x); obs_rows((int)blockIdx.x); obs_store(0); }
         worker_bar();
+        if (my_tiles > 0) embed_publish(0);
 
         long long* dbg = (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ? g_af_dbg : nullptr;
         auto STAMP = [&](int i, int k) { if (dbg && i < 8) dbg[i * 32 + k] = clock64(); };
@@ -313,19 +337,13 @@ act_fused_kernel(ActFusedArgs t) {
             const bool has_next = i + 1 < my_tiles;
             const uint32_t ph = (uint32_t)(i & 1);
             const int buf = i & 1;
-
-            // ---- token embedding -> A operand ----
             float xres[16];
-            embed_row(buf, xres);
-            store_a(sA, xres);
-            fence_async_smem();
-            mbar_arrive(BAR(B_AX0));
             STAMP(i, 1);
             // ---- layer-0 q|k|v: TMEM -> shared memory ----
             WAIT(B_ACC_QKV, ph);
             STAMP(i, 2);
             tc_fence_after();
-            dump_qkv(P_INB0);
+            dump_qkv(P_INB0, 0);
             worker_bar();
             STAMP(i, 3);
             // ---- causal attention, warp = (sequence, head); o -> A operand ----
@@ -336,12 +354,11 @@ act_fused_kernel(ActFusedArgs t) {
                     const int rbase = s * L;
                     att_head(sQKV + rbase * ATT_LD, h, n, lane, [&](int r, int col, float v0, float v1) {
                         if (r < n) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                            uint32_t hi, lo;
+                            split2(v0, v1, hi, lo);
                             uint8_t* d = sA + (col >> 3) * AF_CS + (rbase + r) * 16 + (col & 7) * 2;
-                            *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(h0, h1);
-                            *reinterpret_cast<uint32_t*>(d + AF_AHALF) = pack_bf16x2(l0, l1);
+                            *reinterpret_cast<uint32_t*>(d) = hi;
+                            *reinterpret_cast<uint32_t*>(d + AF_AHALF) = lo;
                         }
                     });
                 }
@@ -355,7 +372,7 @@ act_fused_kernel(ActFusedArgs t) {
             WAIT(B_ACC_OUT, ph);
             STAMP(i, 5);
             tc_fence_after();
-            embed_row(buf, xres);                                  // residual x0 recomputed (cheaper than carrying 16 registers)
+            tmem_ld16(tlane + TM_STASH + (uint32_t)c0, xres);    // residual x0, parked by embed_publish
             res_ln(TM_OUT, P_OUTB0, P_LN1W, P_LN1B, xres);        // xres: x0 -> x1
             store_a(sA, xres);
             fence_async_smem();
@@ -365,7 +382,7 @@ act_fused_kernel(ActFusedArgs t) {
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int m = 2 * i + (c >> 1), s_ = c & 1;
-                WAIT(B_ACC1 + c, ph);
+                WAIT(B_ACC1 + (c >> 1), ph);
                 STAMP(i, 7 + 3 * c);
                 tc_fence_after();
                 float v[16];
@@ -407,7 +424,10 @@ act_fused_kernel(ActFusedArgs t) {
             WAIT(B_ACC_L1, ph);
             STAMP(i, 21);
             tc_fence_after();
-            dump_qkv(P_INB1);
+            // the A operand and TMEM [0,256) are free now: publish the next tile's embedding so its in_proj MMAs (and the weight
+            // loads behind them) run under this tile's last-row attention
+            if (has_next) embed_publish(buf ^ 1);
+            dump_qkv(P_INB1, TM_L1);
             worker_bar();
             STAMP(i, 22);
             {
@@ -482,73 +502,100 @@ act_fused_kernel(ActFusedArgs t) {
     } else if (warp == 16) {
         // =============================================== MMA issuer ===============================================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(TC_M, 64);
             const ChunkDesc dA{umma_desc(smem_u32(sA), AF_CS, 128), umma_desc(smem_u32(sA) + AF_AHALF, AF_CS, 128)};
             const ChunkDesc dA2[2] = {
                 {umma_desc(smem_u32(sA2), AF_CS, 128), umma_desc(smem_u32(sA2) + AF_AHALF, AF_CS, 128)},
                 {umma_desc(smem_u32(sA2) + AF_ASTAGE, AF_CS, 128), umma_desc(smem_u32(sA2) + AF_ASTAGE + AF_AHALF, AF_CS, 128)}};
-            const uint64_t dW0 = umma_desc(smem_u32(sW), 64 * 16, 128);
-            int n = 0, slot = 0;                                   // running weight-chunk counter and its ring slot
-            uint32_t wpar = 0;                                     // parity of the current pass over the ring
-            auto wslot = [&]() -> uint64_t {                       // wait for chunk n, return its B descriptor (hi half)
-                WAIT(B_W_FULL + slot, wpar);
-                return dW0 + (uint64_t)slot * (AF_WCHUNK >> 4);
-            };
-            auto wdone = [&]() {
-                umma_commit(BAR(B_W_EMPTY + slot));
-                ++n; if (++slot == AF_WSLOTS) { slot = 0; wpar ^= 1u; }
-            };
+            // B descriptors (hi half) of the blocks as they sit in the weight buffer
+            const uint32_t sW_u = smem_u32(sW);
+            const uint64_t dW192 = umma_desc(sW_u, 192 * 16, 128);                         // in_proj: slots 0-2
+            const uint64_t dWout = umma_desc(sW_u + 3 * AF_WCHUNK, 64 * 16, 128);          // out_proj: slot 3
+            const uint64_t dWf1a = umma_desc(sW_u, 128 * 16, 128), dWf1b = umma_desc(sW_u + 2 * AF_WCHUNK, 128 * 16, 128);
+            const uint64_t dWf2 = umma_desc(sW_u, 64 * 16, 128);                           // ffn.2 k-chunk k: slot k
             long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0) ? g_af_dbg : nullptr;
             auto STAMP = [&](int i, int k) { if (dbg && i < 8) dbg[i * 32 + k] = clock64(); };
             for (int i = 0; i < my_tiles; ++i) {
                 const uint32_t ph = (uint32_t)(i & 1);
                 WAIT(B_AX0, ph);
                 STAMP(i, 24);
+                WAIT(F_IN0, ph);
                 tc_fence_after();
-                for (int c = 0; c < 3; ++c) { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone(); }
+                mma_block<192>(tmem, dA, dW192, false);
+                umma_commit(BAR(E_IN0));
                 umma_commit(BAR(B_ACC_QKV));
                 STAMP(i, 25);
                 WAIT(B_AO, ph);
                 STAMP(i, 26);
+                WAIT(F_OUT, ph);
                 tc_fence_after();
-                { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + TM_OUT, dA, b, idesc, false); wdone(); }
+                mma_block<64>(tmem + TM_OUT, dA, dWout, false);
+                umma_commit(BAR(E_OUT));
                 umma_commit(BAR(B_ACC_OUT));
                 STAMP(i, 27);
                 WAIT(B_AX1, ph);
                 STAMP(i, 28);
+                WAIT(F_F1A, ph);
                 tc_fence_after();
-                for (int c = 0; c < 4; ++c) {
-                    const uint64_t b = wslot(); tc_fence_after();
-                    mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone();
-                    umma_commit(BAR(B_ACC1 + c));
-                }
+                mma_block<128>(tmem, dA, dWf1a, false);
+                umma_commit(BAR(E_F1A));
+                umma_commit(BAR(B_ACC1));
+                WAIT(F_F1B, ph);
+                tc_fence_after();
+                mma_block<128>(tmem + 128, dA, dWf1b, false);
+                umma_commit(BAR(E_F1B));
+                umma_commit(BAR(B_ACC1 + 1));
                 for (int c = 0; c < 4; ++c) {
                     const int m = 2 * i + (c >> 1), s_ = c & 1;
                     WAIT(B_A2_FULL + s_, (uint32_t)(m & 1));
-                    const uint64_t b = wslot(); tc_fence_after();
-                    mma_chunk(tmem + TM_F2, dA2[s_], b, idesc, c > 0); wdone();
+                    WAIT(F_F2 + c, ph);
+                    tc_fence_after();
+                    mma_block<64>(tmem + TM_F2, dA2[s_], dWf2 + (uint64_t)c * (AF_WCHUNK >> 4), c > 0);
                     umma_commit(BAR(B_A2_EMPTY + s_));
+                    if (c == 2) umma_commit(BAR(E_F2K2));
+                    if (c == 3) umma_commit(BAR(E_F2K3));
                 }
                 umma_commit(BAR(B_ACC_F2));
                 STAMP(i, 29);
                 WAIT(B_AX2, ph);
                 STAMP(i, 30);
+                WAIT(F_IN1, ph);
                 tc_fence_after();
-                for (int c = 0; c < 3; ++c) { const uint64_t b = wslot(); tc_fence_after(); mma_chunk(tmem + (uint32_t)(c * 64), dA, b, idesc, false); wdone(); }
+                mma_block<192>(tmem + TM_L1, dA, dW192, false);
+                umma_commit(BAR(E_IN1));
                 umma_commit(BAR(B_ACC_L1));
                 STAMP(i, 31);
             }
         }
     } else {
         // =============================================== weight producer ===============================================
+        // Every block is loaded as soon as the MMAs that read the slots it overwrites have retired (one E_* wait each):
+        //   in_proj0 -> slots 0-2 | out_proj -> 3 | ffn.0 a -> 0-1, b -> 2-3 | ffn.2 k -> slot k | in_proj1 -> 0-2
         if (lane == 0) {
             const uint8_t* img = t.img[g];
-            const int total = my_tiles * AF_NCHUNK;
-            for (int n = 0; n < total; ++n) {
-                const int s = n % AF_WSLOTS, use = n / AF_WSLOTS;
-                if (use >= 1) WAIT(B_W_EMPTY + s, (uint32_t)((use - 1) & 1));
-                mbar_expect_tx(BAR(B_W_FULL + s), AF_WCHUNK);
-                bulk_g2s(smem_u32(sW) + (uint32_t)s * AF_WCHUNK, img + (size_t)(n % AF_NCHUNK) * AF_WCHUNK, AF_WCHUNK, BAR(B_W_FULL + s));
+            const uint32_t sW_u = smem_u32(sW);
+            auto load = [&](int bar, uint32_t dst_off, uint32_t img_off, uint32_t bytes) {
+                mbar_expect_tx(BAR(bar), bytes);
+                for (uint32_t o = 0; o < bytes; o += 32768u)
+                    bulk_g2s(sW_u + dst_off + o, img + img_off + o, (bytes - o) < 32768u ? (bytes - o) : 32768u, BAR(bar));
+            };
+            for (int i = 0; i < my_tiles; ++i) {
+                const uint32_t ph = (uint32_t)(i & 1);
+                if (i > 0) WAIT(E_IN1, ph ^ 1u);
+                load(F_IN0, 0, IMG_IN0, 3 * AF_WCHUNK);
+                if (i > 0) WAIT(E_F2K3, ph ^ 1u);
+                load(F_OUT, 3 * AF_WCHUNK, IMG_OUT, AF_WCHUNK);
+                WAIT(E_IN0, ph);
+                load(F_F1A, 0, IMG_F1, 2 * AF_WCHUNK);
+                WAIT(E_OUT, ph);
+                load(F_F1B, 2 * AF_WCHUNK, IMG_F1 + 2 * AF_WCHUNK, 2 * AF_WCHUNK);
+                WAIT(E_F1A, ph);
+                load(F_F2 + 0, 0, IMG_F2, AF_WCHUNK);
+                load(F_F2 + 1, AF_WCHUNK, IMG_F2 + AF_WCHUNK, AF_WCHUNK);
+                WAIT(E_F1B, ph);
+                load(F_F2 + 2, 2 * AF_WCHUNK, IMG_F2 + 2 * AF_WCHUNK, AF_WCHUNK);
+                load(F_F2 + 3, 3 * AF_WCHUNK, IMG_F2 + 3 * AF_WCHUNK, AF_WCHUNK);
+                WAIT(E_F2K2, ph);
+                load(F_IN1, 0, IMG_IN1, 3 * AF_WCHUNK);
             }
         }
     }

@@ -86,7 +86,8 @@ __device__ __forceinline__ void att_mtile(const float* __restrict__ sq, int h, i
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+    // three independent accumulators (lo*hi, hi*lo, hi*hi): the P V products of a tile are one dependent chain otherwise
+    float l0 = 0.f, l1 = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f}, o_lh[4] = {0.f, 0.f, 0.f, 0.f}, o_hl[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         if (b < nb_l) {
@@ -100,13 +101,15 @@ __device__ __forceinline__ void att_mtile(const float* __restrict__ sq, int h, i
             uint32_t vh0, vl0, vh1, vl1;
             att_split(vp[0], vh0, vl0);
             att_split(vp[ATT_LD], vh1, vl1);
-            att_mma(o, pl, vh0, vh1);
-            att_mma(o, ph, vl0, vl1);
+            att_mma(o_lh, pl, vh0, vh1);
+            att_mma(o_hl, ph, vl0, vl1);
             att_mma(o, ph, vh0, vh1);
         }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] += o_lh[e] + o_hl[e];
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     out(r0 + g, h * ATT_HD + 2 * t, o[0] * i0, o[1] * i0);
     out(r0 + g + 8, h * ATT_HD + 2 * t, o[2] * i1, o[3] * i1);

@@ -994,18 +994,18 @@ int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab)
         add(lay.layer[i].in_w + (long long)d * d, 2 * d, d);
         add(lay.layer[i].in_w, d, d);
     }
-    // fused acting forward (act_fused.cu): one contiguous image of fifteen [64 x 64] hi+lo chunks in consumption order --
-    // layer-0 in_proj (q, k, v), out_proj, ffn.0 (4 column chunks), ffn.2 (4 k-chunks), layer-1 in_proj (q, k, v)
+    // fused acting forward (act_fused.cu): one contiguous 240 KB image in consumption order -- layer-0 in_proj [192 x 64],
+    // out_proj [64 x 64], ffn.0 as two [128 x 64] halves, ffn.2 as four [64 x 64] k-chunks, layer-1 in_proj [192 x 64]
     tab.act_img_off = -1;
     if (c.n_layers == 2 && d == 64) {
-        auto add64 = [&](long long w_off, int N, int K) {
+        auto addnt = [&](long long w_off, int N, int K, int nt) {
             TcPackEntry& e = tab.e[n++];
-            e.w_off = w_off; e.N = N; e.K = K; e.n_tile = 64; e.pk_off = off;
+            e.w_off = w_off; e.N = N; e.K = K; e.n_tile = nt; e.pk_off = off;
             off += (long long)N * K * 4;
         };
         tab.act_img_off = off;
-        add64(lay.layer[0].in_w, 3 * d, d); add64(lay.layer[0].out_w, d, d); add64(lay.layer[0].f1_w, 4 * d, d);
-        add64(lay.layer[0].f2_w, d, 4 * d); add64(lay.layer[1].in_w, 3 * d, d);
+        addnt(lay.layer[0].in_w, 3 * d, d, 192); addnt(lay.layer[0].out_w, d, d, 64); addnt(lay.layer[0].f1_w, 4 * d, d, 128);
+        addnt(lay.layer[0].f2_w, d, 4 * d, 64); addnt(lay.layer[1].in_w, 3 * d, d, 192);
     }
     tab.n = n; tab.total_bytes = off;
     return 0;
