@@ -129,6 +129,7 @@ act_fused_kernel(ActFusedArgs t) {
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     // bounded wait that never makes a role skip a hand-off: after the first time-out everybody free-runs to the end
     auto WAIT = [&](int b, uint32_t parity) {
+        if (mbar_try_wait(BAR(b), parity)) return;             // fast path: already complete
         if (*s_fail) return;
         if (!mbar_wait(BAR(b), parity)) *s_fail = 1;
     };
@@ -251,6 +252,52 @@ act_fused_kernel(ActFusedArgs t) {
                     }
                 }
             }
+        };
+        // final layer: only k|v of every row and q of each sequence's last valid row are needed (TMEM reads pace the dump)
+        auto dump_kv_qlast = [&](int bias_off, uint32_t tm_base, int buf) {
+            uint32_t r[2][16];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) tmem_ld16_issue(tlane + tm_base + (uint32_t)(64 + cq * 32 + cc * 16), r[cc]);
+            tmem_ld_wait();
+            if (row < AF_QKV_ROWS) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = 64 + cq * 32 + cc * 16;
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sPar + bias_off + col + q);
+                        *reinterpret_cast<float4*>(sQKV + row * ATT_LD + col + q) =
+                            make_float4(__uint_as_float(r[cc][q]) + b.x, __uint_as_float(r[cc][q + 1]) + b.y,
+                                        __uint_as_float(r[cc][q + 2]) + b.z, __uint_as_float(r[cc][q + 3]) + b.w);
+                    }
+                }
+            }
+            if (cq == 0) {                                         // one warp per lane quarter: does a last row live here?
+                const int n0 = sMeta[buf * 2], n1 = sMeta[buf * 2 + 1];
+                const int r0 = n0 > 0 ? n0 - 1 : -1, r1 = n1 > 0 ? L + n1 - 1 : -1;
+                const bool here0 = r0 >= 0 && (r0 >> 5) == q4, here1 = r1 >= 0 && (r1 >> 5) == q4;
+                if (here0 || here1) {                              // warp-uniform
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        tmem_ld16_issue(tlane + tm_base + (uint32_t)(hf * 32), r[0]);
+                        tmem_ld16_issue(tlane + tm_base + (uint32_t)(hf * 32 + 16), r[1]);
+                        tmem_ld_wait();
+                        if (row == r0 || row == r1) {
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                for (int q = 0; q < 16; q += 4) {
+                                    const int col = hf * 32 + cc * 16 + q;
+                                    const float4 b = *reinterpret_cast<const float4*>(sPar + bias_off + col);
+                                    *reinterpret_cast<float4*>(sQKV + row * ATT_LD + col) =
+                                        make_float4((__uint_as_float(r[cc][q]) + b.x) * qs, (__uint_as_float(r[cc][q + 1]) + b.y) * qs,
+                                                    (__uint_as_float(r[cc][q + 2]) + b.z) * qs, (__uint_as_float(r[cc][q + 3]) + b.w) * qs);
+                                }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
         };
         // y = LayerNorm(x + relu(acc + b)) over the 64 columns of `row` (4 threads x 16 columns, reduced through smem);
         // the residual x lives in this thread's registers from the phase that produced it and is replaced by y
@@ -427,7 +474,7 @@ act_fused_kernel(ActFusedArgs t) {
             // the A operand and TMEM [0,256) are free now: publish the next tile's embedding so its in_proj MMAs (and the weight
             // loads behind them) run under this tile's last-row attention
             if (has_next) embed_publish(buf ^ 1);
-            dump_qkv(P_INB1, TM_L1);
+            dump_kv_qlast(P_INB1, TM_L1, buf);
             worker_bar();
             STAMP(i, 22);
             {
