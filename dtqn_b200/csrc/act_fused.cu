@@ -46,7 +46,7 @@ static_assert(AF_R_BYTES >= 2 * AF_ASTAGE, "hidden operand ring must fit in the 
 
 // parameter vectors staged in shared memory (float offsets)
 enum { P_INB0 = 0, P_OUTB0 = 192, P_LN1W = 256, P_LN1B = 320, P_F1B = 384, P_F2B = 640, P_LN2W = 704, P_LN2B = 768,
-       P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_POS = 1344 /* [L][64] position table */, P_TOTAL = 1344 + AF_MAX_L * 64 };
+       P_INB1 = 832, P_EW = 1024, P_EB = 1280, P_POS = 1344 /* [L][68] position table, rows padded: conflict-free float4 per row */, P_TOTAL = 1344 + AF_MAX_L * 68 };
 
 // weight buffer hand-offs (each barrier completes once per tile): F_* "landed" (TMA complete_tx), E_* "consumed" (tcgen05.commit)
 enum { F_IN0 = 0, F_OUT, F_F1A, F_F1B, F_F2 /* +k */, F_IN1 = F_F2 + 4, E_IN0, E_OUT, E_F1A, E_F1B, E_F2K2, E_F2K3, E_IN1,
@@ -148,7 +148,7 @@ act_fused_kernel(ActFusedArgs t) {
         else if (e < P_EW) v = __ldg(p + t.l1.in_b + (e - P_INB1));
         else if (e < P_EB) { const int c = (e - P_EW) >> 2, k = (e - P_EW) & 3; v = k < t.O ? __ldg(p + t.emb_w + c * t.O + k) : 0.f; }
         else if (e < P_POS) v = __ldg(p + t.emb_b + (e - P_EB));
-        else v = (e - P_POS) < L * 64 ? __ldg(p + t.pos + (e - P_POS)) : 0.f;
+        else { const int r = (e - P_POS) / 68, c = (e - P_POS) % 68; v = (r < L && c < 64) ? __ldg(p + t.pos + r * 64 + c) : 0.f; }
         sPar[e] = v;
     }
     if (tid == 0) {
@@ -345,7 +345,7 @@ act_fused_kernel(ActFusedArgs t) {
 #pragma unroll
             for (int q = 0; q < 16; q += 4) {
                 float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (real) pv = *reinterpret_cast<const float4*>(sPar + P_POS + jrow * 64 + c0 + q);
+                if (real) pv = *reinterpret_cast<const float4*>(sPar + P_POS + jrow * 68 + c0 + q);
                 const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
                 const float4 b4 = *reinterpret_cast<const float4*>(sPar + P_EB + c0 + q);
                 const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
