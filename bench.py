@@ -216,29 +216,41 @@ def main():
     grad_sps = args.steps / (ms / 1e3)
 
     # ---- e2e: the same loop driven through the host-facing API with HOST buffers (pinned), copies inside the timing ----
-    q_host = torch.empty((N, tr.env.num_actions), dtype=torch.float32, pin_memory=True)
-    act_host = torch.empty((N,), dtype=torch.int32, pin_memory=True)
-    obs_host = torch.empty((N, tr.env.obs_dim), dtype=torch.float32, pin_memory=True)
-    rew_host = torch.empty((N,), dtype=torch.float32, pin_memory=True)
-    done_host = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
-    loss_host = torch.empty((8,), dtype=torch.float32, pin_memory=True)
     hrng = np.random.default_rng(1234 + rank)
-    h2d = act_host.numel() * 4
-    d2h = q_host.numel() * 4 + obs_host.numel() * 4 + rew_host.numel() * 4 + done_host.numel() + loss_host.numel() * 4
+    A = tr.env.num_actions
+    h2d = N * 4
+    d2h = N * A * 4 + N * tr.env.obs_dim * 4 + N * 4 + N + 8 * 4
+    if use_graph:
+        tr.enable_host_loop()
 
-    def e2e_step(eps):
-        q = tr.agent.q_last_batched()                              # acting forward on the device context
-        q_host.copy_(q, non_blocking=True); torch.cuda.synchronize()
-        greedy = q_host.numpy().argmax(1).astype(np.int32)          # host-side epsilon-greedy (user policy code)
-        explore = hrng.random(N) < eps
-        act_host.numpy()[:] = np.where(explore, hrng.integers(0, tr.env.num_actions, N), greedy)
-        tr.env.step(actions=act_host.to(dev, non_blocking=True), mode=_lib.ACT_GIVEN)
-        obs_host.copy_(tr.env.obs_out, non_blocking=True); rew_host.copy_(tr.env.reward_out, non_blocking=True)
-        done_host.copy_(tr.env.done_out, non_blocking=True)
-        tr.agent.train()
-        loss_host.copy_(tr.agent.stats, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(loss_host[0])
+        def e2e_step(eps):
+            q = tr.host_q()                                             # acting forward (graph) -> pinned host Q, sync
+            greedy = q.numpy().argmax(1).astype(np.int32)               # host-side epsilon-greedy (user policy code)
+            explore = hrng.random(N) < eps
+            tr.h_act.numpy()[:] = np.where(explore, hrng.integers(0, A, N), greedy)
+            tr.host_step(tr.h_act)                                      # H2D actions, env step + appends, D2H obs / reward / done
+            return float(tr.host_train()[0])                            # train step (graph), D2H statistics, sync
+    else:
+        q_host = torch.empty((N, A), dtype=torch.float32, pin_memory=True)
+        act_host = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+        obs_host = torch.empty((N, tr.env.obs_dim), dtype=torch.float32, pin_memory=True)
+        rew_host = torch.empty((N,), dtype=torch.float32, pin_memory=True)
+        done_host = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
+        loss_host = torch.empty((8,), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step(eps):
+            q = tr.agent.q_last_batched()                              # acting forward on the device context
+            q_host.copy_(q, non_blocking=True); torch.cuda.synchronize()
+            greedy = q_host.numpy().argmax(1).astype(np.int32)          # host-side epsilon-greedy (user policy code)
+            explore = hrng.random(N) < eps
+            act_host.numpy()[:] = np.where(explore, hrng.integers(0, A, N), greedy)
+            tr.env.step(actions=act_host.to(dev, non_blocking=True), mode=_lib.ACT_GIVEN)
+            obs_host.copy_(tr.env.obs_out, non_blocking=True); rew_host.copy_(tr.env.reward_out, non_blocking=True)
+            done_host.copy_(tr.env.done_out, non_blocking=True)
+            tr.agent.train()
+            loss_host.copy_(tr.agent.stats, non_blocking=True)
+            torch.cuda.synchronize()
+            return float(loss_host[0])
 
     if use_graph:
         tr.disable_graphs()
@@ -373,8 +385,10 @@ def main():
                                            "p2p-fused": "own kernel: flag barrier + NVLink peer reads + norm, then clip/Adam "
                                                         "(inside the CUDA graph, no NCCL call)"}[tr.allreduce]},
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
-                                                "host obs/reward/done -> agent.train -> host loss"},
+                    "steps": e2e_steps, "api": ("BatchedTrainer.host_q (graph, D2H Q) -> host eps-greedy -> host_step(pinned actions: H2D, env graph, D2H "
+                                            "obs/reward/done) -> host_train (graph, D2H statistics)") if use_graph else
+                                           ("agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
+                                            "host obs/reward/done -> agent.train -> host loss")},
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "breakdown": breakdown,
             "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,

@@ -147,6 +147,61 @@ class BatchedTrainer:
         self.eps.anneal()
         self.iterations += 1
 
+    # ---- host-policy loop: the user's policy code runs on the HOST between device calls ------------------------------------------
+    def enable_host_loop(self) -> None:
+        """Prepare ``host_q / host_step / host_train``: pinned host buffers plus three CUDA graphs (acting forward; env step
+        + replay / context append + roll for host-chosen actions; sample + gather + 3 forwards + TD + backward + update),
+        so each call is one graph replay and the copies it documents.  Needs a sampleable replay (prepopulate first).
+        Capturing runs each piece once for real (one acting forward, one env step with the current ``env.actions``, one
+        update)."""
+        assert self.agent.replay_buffer.can_sample(self.agent.batch_size), "prepopulate before enable_host_loop()"
+        env, agent, N = self.env, self.agent, self.n_envs
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        self.h_q, self.h_act = pin((N, env.num_actions), torch.float32), pin((N,), torch.int32)
+        self.h_obs, self.h_rew = pin((N, env.obs_dim), torch.float32), pin((N,), torch.float32)
+        self.h_done, self.h_stats = pin((N,), torch.uint8), pin((8,), torch.float32)
+        agent.eval_off()
+        self._hg_q = self.capture(agent.q_last_batched)
+        self._hg_env = self.capture(lambda: env.step(mode=_lib.ACT_GIVEN))        # reads env.actions
+        if self._update_in_graph:
+            self._hg_train = self.capture(self.train_only)
+        else:                                                                      # NCCL allreduce stays outside the graph
+            def fb():
+                rb = agent.replay_buffer
+                eps, starts = rb.draw_indices(agent.batch_size)
+                rb.gather_windows(eps, starts, out=agent._win)
+                agent.forward_backward(*agent._win[:4])
+            self._hg_train = self.capture(fb)
+            agent.reduce_and_step()
+        agent.finish_step()                                   # the capture warm-up performed one real update
+
+    def host_q(self) -> torch.Tensor:
+        """Q of every env's last context position as a pinned HOST tensor [n_envs, A] (agents/dtqn.py:81-107 batched)."""
+        self._hg_q.replay()
+        self.h_q.copy_(self.agent._q_last, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_q
+
+    def host_step(self, actions: torch.Tensor):
+        """env.step + agent.observe for host-chosen actions (int32 [n_envs], ideally pinned).  Returns pinned host
+        (obs, reward, done); they are complete after the next synchronising call (``host_train`` / ``host_q``)."""
+        self.env.actions.copy_(actions, non_blocking=True)
+        self._hg_env.replay()
+        self.h_obs.copy_(self.env.obs_out, non_blocking=True)
+        self.h_rew.copy_(self.env.reward_out, non_blocking=True)
+        self.h_done.copy_(self.env.done_out, non_blocking=True)
+        return self.h_obs, self.h_rew, self.h_done
+
+    def host_train(self) -> torch.Tensor:
+        """agent.train() (agents/dtqn.py:162-269); returns the step's 8 statistics (loss first) as a pinned host tensor."""
+        self._hg_train.replay()
+        if not self._update_in_graph:
+            self.agent.reduce_and_step()
+        self.agent.finish_step()
+        self.h_stats.copy_(self.agent.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_stats
+
     def save_checkpoint(self, checkpoint_dir: str, wandb_id: Optional[str] = None, episode_successes=None,
                         episode_rewards=None, episode_lengths=None) -> None:
         """agent.save_checkpoint (dqn.py:222-279) + env streams, contexts and loop counters; one set of files per rank

@@ -85,3 +85,33 @@ def test_host_call_api_single_env():
     assert episodes >= 6 and agent.num_train_steps > 0
     agent.check_finite()
     assert agent.replay_buffer.pos[0] == episodes
+
+
+def test_host_loop_graphs_match_eager_api():
+    """BatchedTrainer.host_q / host_step / host_train (three CUDA graphs + pinned host buffers) against the same calls made
+    eagerly through the agent / env API with the same host-chosen actions."""
+    from dtqn_b200 import _lib
+    a, b = _trainer(n_envs=256, batch=8), _trainer(n_envs=256, batch=8)
+    for t in (a, b):
+        t.prepopulate(230)
+    b.enable_host_loop()
+    # the three capture warm-ups of b executed one acting forward, one env step (with b.env.actions) and one train step
+    a.agent.q_last_batched()
+    a.env.step(actions=b.env.actions.clone(), mode=_lib.ACT_GIVEN)
+    a.agent.train()
+    rng = np.random.default_rng(0)
+    for it in range(6):
+        qa = a.agent.q_last_batched().cpu().numpy()
+        qb = b.host_q().numpy().copy()
+        assert np.abs(qa - qb).max() <= 2e-5 * max(1.0, np.abs(qa).max()), it
+        act = torch.from_numpy(np.where(rng.random(256) < 0.3, rng.integers(0, 3, 256), qb.argmax(1)).astype(np.int32))
+        a.env.step(actions=act.cuda(), mode=_lib.ACT_GIVEN)
+        obs, rew, done = b.host_step(act.pin_memory())
+        a.agent.train()
+        stats = b.host_train().numpy().copy()
+        assert np.array_equal(obs.numpy(), a.env.obs_out.cpu().numpy()) and np.array_equal(done.numpy(), a.env.done_out.cpu().numpy())
+        assert np.array_equal(rew.numpy(), a.env.reward_out.cpu().numpy())
+        assert np.allclose(stats, a.agent.stats.cpu().numpy(), rtol=1e-3, atol=1e-5), (it, stats, a.agent.stats)
+    assert np.array_equal(a.env.rng_state(), b.env.rng_state())
+    assert a.agent.num_train_steps == b.agent.num_train_steps
+    assert (a.agent.policy_network.flat - b.agent.policy_network.flat).abs().max().item() < 5e-5
