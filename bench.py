@@ -31,6 +31,24 @@ CTX, EMBED, HEADS, LAYERS, BATCH = 50, 64, 8, 2, 32
 FWD_FLOP_PER_TOKEN = 231_168          # SURVEY.md section 8d, CarFlag d=64 L=50
 
 
+# stdout carries exactly ONE JSON line: everything else a library prints there (NCCL banners, warnings) goes to stderr
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -393,10 +411,11 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "breakdown": breakdown,
             "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
