@@ -322,6 +322,19 @@ def main():
                 roof = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                         "launches_timed": v["n"], "avg_us_per_launch": 1e3 * v["ms"] / v["n"]}
+            if nm == "act_fused_tcgen05":
+                try:
+                    with open(os.path.join(ROOT, "profiles", "r1_act_fused_ncu.json")) as f:
+                        aj = json.load(f)
+                    roof["traffic"] = aj["dram_bytes_read_per_launch"] + aj["dram_bytes_write_per_launch"]
+                    roof["traffic_note"] = ("dram__bytes_read + write of one launch (ncu --set full, profiles/r1_act_fused_ncu.json): the "
+                                            "context rows and the weight image; every activation stays in shared memory / TMEM")
+                    roof["tensor_view"] = {"sm__pipe_tensor_cycles_active_pct": aj["sm__pipe_tensor_cycles_active_pct"],
+                                           "note": "achieved = ALGORITHMIC FLOPs (embed + layer 0 + final-layer in_proj + last-row attention) / "
+                                                   "launch time; the bf16 hi/lo split issues 3 MMAs per algorithmic MMA, so this fraction is "
+                                                   "capped at 1/3, and the attention core runs on mma.sync (TF32 x3), not on tcgen05"}
+                except Exception:
+                    pass
             try:
                 with open(os.path.join(ROOT, "profiles", "r1_linear_traffic.json")) as f:
                     tj = json.load(f)
