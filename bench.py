@@ -57,9 +57,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="lockstep envs per GPU")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--workload", default="carflag", choices=["carflag", "memory"],
+                    help="carflag: BASELINE.json configs[1] (the headline); memory: configs[2] (Memory-5-v0, in-embed 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.workload == "memory":
+        global ENV_ID, EMBED, FWD_FLOP_PER_TOKEN
+        ENV_ID, EMBED, FWD_FLOP_PER_TOKEN = "Memory-5-v0", 128, 893_440      # SURVEY.md section 8d, Memory d=128 L=50
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -346,7 +352,7 @@ def main():
                                             "in the 126 MB L2 when the kernel ends" % round(v["n"] / psteps))
                     # the GEMMs have K = 64..256: 24-64 FLOP per byte against a machine balance of ~220 -> HBM-bound by the roofline
                     # model; the tensor-pipe view of the same launches (2*M*N*K per launch, x3 issued for the bf16 hi/lo split):
-                    flops = FWD_FLOP_PER_TOKEN and (2.0 * N * CTX * (64 * 192 + 64 * 64 + 64 * 256 + 256 * 64 + 64 * 128))
+                    flops = 2.0 * N * CTX * EMBED * EMBED * (3 + 1 + 4 + 4 + 2)
                     roof["tensor_view"] = {"algorithmic_TFLOPs": flops * psteps / (v["ms"] * 1e-3) / 1e12,
                                            "of_sustained_bf16_peak": flops * psteps / (v["ms"] * 1e-3) / 1e12 / pk["tf_sustained"],
                                            "note": "3 MMAs issued per algorithmic MMA (bf16 hi/lo split): utilisation on algorithmic FLOPs is capped at 1/3"}
