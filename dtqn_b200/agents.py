@@ -142,7 +142,12 @@ class DtqnAgent:
     def target_update(self) -> None:
         """Hard update (dqn.py:208-210): one flat device-to-device copy."""
         self.target_network.flat.copy_(self.policy_network.flat)
-        self.target_network.packed_stale = True
+        # the weight images (tcgen05 operands + the k-major copies the training forward streams) must follow even when the
+        # loop runs as graph replays, where forward_groups' host-side staleness check never executes
+        if self.policy_network.packed_stale:
+            self.policy_network.repack()
+        self.target_network.packed.copy_(self.policy_network.packed)
+        self.target_network.packed_stale = False
 
     # ---- checkpoint / resume (dqn.py:212-327; file format in dtqn_b200/checkpoint.py) ----------------------------------------
     def save_mini_checkpoint(self, checkpoint_dir: str, wandb_id: Optional[str]) -> None:

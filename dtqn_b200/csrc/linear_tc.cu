@@ -25,6 +25,15 @@ namespace {
 // W[N, K] fp32 row-major -> blocks [n_tile][k_chunk] of { hi[8][N_TILE][8 bf16], lo[8][N_TILE][8 bf16] }.
 __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, TcPackTable tab) {
     const TcPackEntry e = tab.e[blockIdx.y];
+    if (e.n_tile == 0) {                                       // fp32 transpose: out[k][n] = W[n][k]
+        float* out = reinterpret_cast<float*>(packed + e.pk_off);
+        const long long total = (long long)e.N * e.K;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+            const int k = (int)(idx / e.N), n = (int)(idx % e.N);
+            out[idx] = params[e.w_off + (long long)n * e.K + k];
+        }
+        return;
+    }
     const int NT = e.n_tile;
     const long long chunks = (long long)e.N * (e.K / 8);          // 16-byte chunks per half
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (long long)gridDim.x * blockDim.x) {
@@ -1006,6 +1015,22 @@ int tc_pack_table(const dtqn_net_cfg& c, const NetLayout& lay, TcPackTable& tab)
         tab.act_img_off = off;
         addnt(lay.layer[0].in_w, 3 * d, d, 192); addnt(lay.layer[0].out_w, d, d, 64); addnt(lay.layer[0].f1_w, 4 * d, d, 128);
         addnt(lay.layer[0].f2_w, d, 4 * d, 64); addnt(lay.layer[1].in_w, 3 * d, d, 192);
+    }
+    // k-major fp32 copies for the sequence-resident training forward (net_seq.cu): per layer in_proj | out_proj | ffn.0 |
+    // ffn.2 (12 d^2 floats), then the head's ffn.0
+    tab.wt_off = -1;
+    if (d == 64) {
+        auto addt = [&](long long w_off, int N, int K) {
+            TcPackEntry& e = tab.e[n++];
+            e.w_off = w_off; e.N = N; e.K = K; e.n_tile = 0; e.pk_off = off;
+            off += (long long)N * K * 4;
+        };
+        tab.wt_off = off;
+        for (int i = 0; i < c.n_layers; ++i) {
+            const LayerOff& l = lay.layer[i];
+            addt(l.in_w, 3 * d, d); addt(l.out_w, d, d); addt(l.f1_w, 4 * d, d); addt(l.f2_w, d, 4 * d);
+        }
+        addt(lay.h1_w, d, d);
     }
     tab.n = n; tab.total_bytes = off;
     return 0;

@@ -3,7 +3,8 @@
 #include "net.cuh"
 
 struct TcPackEntry { long long w_off, pk_off; int N, K, n_tile; };
-struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1 + 5]; int n; long long total_bytes, act_img_off; };
+// n_tile == 0: plain fp32 TRANSPOSE of the weight ([K][N], k-major) for the sequence-resident kernel's cp.async slabs
+struct TcPackTable { TcPackEntry e[6 * DTQN_MAX_LAYERS + 1 + 5 + 4 * DTQN_MAX_LAYERS + 1]; int n; long long total_bytes, act_img_off, wt_off; };
 
 // entry order: per layer in_proj, out_proj, ffn.0, ffn.2; then the head's ffn.0; then per layer the K|V rows and the Q rows
 // of in_proj (index 4*n_layers + 1 + 2*i, + 1)

@@ -112,5 +112,7 @@ struct LinArgs {
 
 // sequence-resident fused forward (net_seq.cu)
 bool seq_forward_supported(const dtqn_net_cfg& c, int L);
+// wt: per-group k-major fp32 weight copies (TcPackTable::wt_off region of the packed image) or all-NULL -> weights are read
+// (and transposed on the fly) from the flat parameters
 int launch_seq_forward(const dtqn_net_cfg& c, const NetLayout& lay, const NetAct& act, const GroupPtrs& P, int G, int n_seq,
-                       int L, int save, float* q_out, cudaStream_t st);
+                       int L, int save, float* q_out, cudaStream_t st, const float* const* wt = nullptr);

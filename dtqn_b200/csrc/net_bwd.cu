@@ -73,14 +73,16 @@ td_loss_kernel(const float* __restrict__ q_all, const uint8_t* __restrict__ act_
 }
 
 // ---- head (ffn.2) backward: N = A is tiny -> CUDA cores --------------------------------------------------------------------
-// d_hh = (dq W2) * [hh > 0];  dW2 += dq^T hh;  db2 += colsum(dq).   64 tokens per CTA.
+// d_hh = (dq W2) * [hh > 0];  dW2 += dq^T hh;  db2 += colsum(dq).   HB_TOK tokens per CTA (few CTAs on purpose: the fp32 atomics into
+// gW2 are the least reproducible part of the update, and Q -- hence the greedy action -- reads W2 directly).
+#define HB_TOK 64
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, const float* __restrict__ W2, int T, int d,
                 int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2) {
-    __shared__ float sdq[64][33];
-    const int t0 = blockIdx.x * 64;
-    const int nt = min(64, T - t0);
-    for (int e = threadIdx.x; e < 64 * A; e += blockDim.x) {
+    __shared__ float sdq[HB_TOK][33];
+    const int t0 = blockIdx.x * HB_TOK;
+    const int nt = min(HB_TOK, T - t0);
+    for (int e = threadIdx.x; e < HB_TOK * A; e += blockDim.x) {
         const int r = e / A, a = e % A;
         sdq[r][a] = r < nt ? dq[(long long)(t0 + r) * A + a] : 0.f;
     }
@@ -489,7 +491,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     DTQN_LAUNCH_CHECK();
     // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
     prof_begin(PROF_HEAD, st);
-    head_bwd_kernel<<<dtqn_cdiv(T0, 64), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
+    head_bwd_kernel<<<dtqn_cdiv(T0, HB_TOK), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
                                                         grads + lay.h2_w, grads + lay.h2_b);
     prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();

@@ -648,8 +648,17 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         prof_end(PROF_EMBED, st, 2.0 * (double)T * lay.k_in * d);
         DTQN_LAUNCH_CHECK();
     }
-    if (!use_tc && q_mode == 0 && g_seq_fused && seq_forward_supported(*cfg, L))
-        return launch_seq_forward(*cfg, lay, act, P, G, n_seq, L, save, q_out, st);   // all layers + head, one launch
+    if (!use_tc && q_mode == 0 && g_seq_fused && seq_forward_supported(*cfg, L)) {     // all layers + head, one launch
+        const float* wt[DTQN_MAX_GROUPS] = {nullptr, nullptr, nullptr};
+        bool have_wt = packed != nullptr;
+        TcPackTable tb{};
+        if (have_wt) { tc_pack_table(*cfg, lay, tb); have_wt = tb.wt_off >= 0; }
+        for (int g = 0; g < G && have_wt; ++g) {
+            if (!pk[g]) have_wt = false;
+            else wt[g] = reinterpret_cast<const float*>(pk[g] + tb.wt_off);
+        }
+        return launch_seq_forward(*cfg, lay, act, P, G, n_seq, L, save, q_out, st, have_wt ? wt : nullptr);
+    }
     const float* x_in = act.x0;
     // acting (q_mode 1) needs the final layer's output at ONE position per sequence: that layer only projects K/V for
     // every token; its query, attention row, out_proj, FFN and LayerNorms run on n_seq rows (exactly the same values).

@@ -15,12 +15,13 @@ constexpr int LDQ = 3 * SQ_D + 4;      // sQKV row stride: float4-aligned rows f
 constexpr int LDH = 4 * SQ_D + 1;      // sH row stride
 constexpr int SW_LD = 256 + 4;         // weight slab row stride (max N = 256)
 
+constexpr int SW_STAGES = 3;           // cp.async ring of weight slabs
 struct SeqSmem {
     float x[SQ_ROWS * LDX];            // layer input (residual of LN1)
     float o[SQ_ROWS * LDX];            // attention output, then x1 (residual of LN2)
     float qkv[(SQ_ROWS + 4) * LDQ];    // packed q | k | v; 4 zero rows so a key block may run past the last key
     float h[SQ_ROWS * LDH];            // FFN hidden
-    float w[16 * SW_LD];               // transposed weight slab [16 k][N]
+    float w[SW_STAGES * 16 * SW_LD];   // weight slabs [16 k][N] (k-major), 3-stage ring
 };
 
 __device__ __forceinline__ int sq_col(int tx, int j) { return (j >> 2) * 64 + tx * 4 + (j & 3); }
@@ -70,6 +71,62 @@ __device__ __forceinline__ void cta_gemm64(const float* __restrict__ sA, int lda
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
     }
+}
+
+// Same contraction with the weights read from the K-MAJOR copy WT[K][N] (pack_weights_kernel): slabs of 16 k-rows are
+// contiguous rows of N floats, so they stream through a 3-stage cp.async ring (two slabs in flight while one is consumed,
+// one __syncthreads per slab) instead of load -> transpose -> store with the latency of every slab exposed.  The FMA order
+// per output element is unchanged (k ascending), so the results are bit-identical to cta_gemm64.
+__device__ __forceinline__ void sq_cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cta_gemm64_pipe(const float* __restrict__ sA, int lda, const float* __restrict__ WT, int K,
+                                                float (&acc)[4][N / 16], float* __restrict__ sW) {
+    constexpr int TN = N / 16, WV = N / 64;                   // 16-byte copies of a [16 x N] slab per thread
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const int slabs = K / 16;
+    auto issue = [&](int s) {
+        if (s < slabs) {
+            float* dst = sW + (s % SW_STAGES) * (16 * SW_LD);
+            const float* src = WT + (size_t)s * 16 * N;
+#pragma unroll
+            for (int v = 0; v < WV; ++v) {
+                const int idx = tid + v * SQ_THREADS, kr = idx / (N / 4), nq = idx % (N / 4);
+                sq_cp_async16(dst + kr * SW_LD + nq * 4, src + (size_t)kr * N + nq * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    issue(1);
+    for (int s = 0; s < slabs; ++s) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // slab s has landed (this thread's copies)
+        __syncthreads();                                      // ... everybody's; slab s - 1 fully consumed; sA writes ordered
+        issue(s + 2);                                         // refill the slot slab s - 1 used
+        const float* sWs = sW + (s % SW_STAGES) * (16 * SW_LD);
+        const int k0 = s * 16;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[TN];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[(ty * 4 + i) * lda + k0 + kk];
+#pragma unroll
+            for (int j4 = 0; j4 < TN / 4; ++j4) {
+                const float4 bv = *reinterpret_cast<const float4*>(&sWs[kk * SW_LD + j4 * 64 + tx * 4]);
+                b[j4 * 4] = bv.x; b[j4 * 4 + 1] = bv.y; b[j4 * 4 + 2] = bv.z; b[j4 * 4 + 3] = bv.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float sq_ex2(float x) {
@@ -175,6 +232,7 @@ struct SeqFwdArgs {
     NetAct act;                        // global activation buffers ([G * n_seq * L, width]); x0 is the input
     int n_layers, n_seq, L, A, save;
     float* q_out;                      // [G, n_seq, L, A]
+    const float* wt[DTQN_MAX_GROUPS];  // k-major weight copies (nullable): layer i at 12 d^2 i: in | out | ffn.0 | ffn.2; head ffn.0 last
 };
 
 // y = LayerNorm(xres + relu(acc + bias)) for the 4 rows x 4 cols this thread holds of a [64 x 64] tile; the 16 lanes that
@@ -226,6 +284,8 @@ seq_forward_kernel(SeqFwdArgs a) {
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int seq = blockIdx.x, g = seq / a.n_seq, L = a.L;
     const float* p = a.P.p[g];
+    const float* wt = a.wt[g];                                // k-major weight copies, or NULL
+    constexpr int D2 = SQ_D * SQ_D;
     const size_t t0 = (size_t)seq * L;                        // first token row of this sequence in every activation buffer
     const float scale = 1.0f / sqrtf((float)SQ_HD);
 
@@ -243,7 +303,8 @@ seq_forward_kernel(SeqFwdArgs a) {
         // ---- in_proj: qkv = x W_in^T + b_in ----
         {
             float acc[4][12];
-            cta_gemm64<192>(sm.x, LDX, p + lo.in_w, SQ_D, acc, sm.w);
+            if (wt) cta_gemm64_pipe<192>(sm.x, LDX, wt + (size_t)li * 12 * D2, SQ_D, acc, sm.w);
+            else cta_gemm64<192>(sm.x, LDX, p + lo.in_w, SQ_D, acc, sm.w);
 #pragma unroll
             for (int j4 = 0; j4 < 3; ++j4) {
                 float bias[4];
@@ -266,7 +327,8 @@ seq_forward_kernel(SeqFwdArgs a) {
         // ---- out_proj -> relu -> +x -> LN1  (x1 overwrites the attention output tile) ----
         {
             float acc[4][4];
-            cta_gemm64<64>(sm.o, LDX, p + lo.out_w, SQ_D, acc, sm.w);
+            if (wt) cta_gemm64_pipe<64>(sm.o, LDX, wt + (size_t)li * 12 * D2 + 3 * D2, SQ_D, acc, sm.w);
+            else cta_gemm64<64>(sm.o, LDX, p + lo.out_w, SQ_D, acc, sm.w);
             __syncthreads();                                  // every thread is done reading sm.o as the A operand
             sq_res_ln(acc, p, lo.out_b, lo.ln1_w, lo.ln1_b, sm.x, sm.o, L, la.x1 + t0 * SQ_D,
                       a.save ? la.r1 + t0 * SQ_D : nullptr, a.save ? la.st1 + t0 * 2 : nullptr);
@@ -275,7 +337,8 @@ seq_forward_kernel(SeqFwdArgs a) {
         // ---- ffn.0 + relu -> h ----
         {
             float acc[4][16];
-            cta_gemm64<256>(sm.o, LDX, p + lo.f1_w, SQ_D, acc, sm.w);
+            if (wt) cta_gemm64_pipe<256>(sm.o, LDX, wt + (size_t)li * 12 * D2 + 4 * D2, SQ_D, acc, sm.w);
+            else cta_gemm64<256>(sm.o, LDX, p + lo.f1_w, SQ_D, acc, sm.w);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 float bias[4];
@@ -295,7 +358,8 @@ seq_forward_kernel(SeqFwdArgs a) {
         // ---- ffn.2 -> relu -> +x1 -> LN2 -> next layer input (sX) ----
         {
             float acc[4][4];
-            cta_gemm64<64>(sm.h, LDH, p + lo.f2_w, 4 * SQ_D, acc, sm.w);
+            if (wt) cta_gemm64_pipe<64>(sm.h, LDH, wt + (size_t)li * 12 * D2 + 8 * D2, 4 * SQ_D, acc, sm.w);
+            else cta_gemm64<64>(sm.h, LDH, p + lo.f2_w, 4 * SQ_D, acc, sm.w);
             sq_res_ln(acc, p, lo.f2_b, lo.ln2_w, lo.ln2_b, sm.o, sm.x, L, la.x2 + t0 * SQ_D,
                       a.save ? la.r2 + t0 * SQ_D : nullptr, a.save ? la.st2 + t0 * 2 : nullptr);
         }
@@ -304,7 +368,8 @@ seq_forward_kernel(SeqFwdArgs a) {
     // ---- Q head: hh = relu(x W1^T + b1); q = hh W2^T + b2 ----
     {
         float acc[4][4];
-        cta_gemm64<64>(sm.x, LDX, p + a.lay.h1_w, SQ_D, acc, sm.w);
+        if (wt) cta_gemm64_pipe<64>(sm.x, LDX, wt + (size_t)a.n_layers * 12 * D2, SQ_D, acc, sm.w);
+        else cta_gemm64<64>(sm.x, LDX, p + a.lay.h1_w, SQ_D, acc, sm.w);
         float bias[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) bias[e] = __ldg(p + a.lay.h1_b + tx * 4 + e);
@@ -334,10 +399,11 @@ bool seq_forward_supported(const dtqn_net_cfg& c, int L) {
 }
 
 int launch_seq_forward(const dtqn_net_cfg& c, const NetLayout& lay, const NetAct& act, const GroupPtrs& P, int G, int n_seq,
-                       int L, int save, float* q_out, cudaStream_t st) {
+                       int L, int save, float* q_out, cudaStream_t st, const float* const* wt) {
     SeqFwdArgs a{};
     a.P = P; a.lay = lay; a.act = act; a.n_layers = c.n_layers; a.n_seq = n_seq; a.L = L; a.A = c.num_actions; a.save = save;
     a.q_out = q_out;
+    for (int g = 0; g < G; ++g) a.wt[g] = wt ? wt[g] : nullptr;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(seq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));

@@ -14,8 +14,11 @@ def _trainer(**kw):
     return BatchedTrainer(**args)
 
 
-def test_graph_replay_matches_eager():
-    a, b = _trainer(), _trainer()
+@pytest.mark.parametrize("tuf", [10_000, 4])
+def test_graph_replay_matches_eager(tuf):
+    """tuf = 4: three hard target updates inside the window -- the target's weight images (which the graph's training forward
+    streams) must follow the host-side target_update between replays."""
+    a, b = _trainer(tuf=tuf), _trainer(tuf=tuf)
     for t in (a, b):
         t.prepopulate(230)
         assert t.agent.replay_buffer.can_sample(16)
@@ -29,6 +32,11 @@ def test_graph_replay_matches_eager():
     assert torch.isfinite(pa).all() and torch.isfinite(pb).all()
     # identical algorithm and random streams; only fp32 atomic accumulation order differs
     assert (pa - pb).abs().max().item() < 5e-5
+    assert (a.agent.target_network.flat - b.agent.target_network.flat).abs().max().item() < 5e-5
+    if tuf == 4:      # the image the graph streams for the target network == a fresh pack of its current parameters
+        img = b.agent.target_network.packed.clone()
+        b.agent.target_network.repack(); torch.cuda.synchronize()
+        assert torch.equal(img, b.agent.target_network.packed)
     assert np.array_equal(a.env.rng_state(), b.env.rng_state())
     assert abs(a.agent.td_errors.mean() - b.agent.td_errors.mean()) < 1e-4
     assert int(a.agent.opt_step.item()) == 13 and int(b.agent.opt_step.item()) == 13
