@@ -208,6 +208,9 @@ int dtqn_set_attn_mma(int32_t on);
  * and the attention row of the last valid position as ONE persistent tcgen05 kernel per 128-token tile (no activations
  * in HBM); 0: one kernel per GEMM / attention. */
 int dtqn_set_act_fused(int32_t on);
+/* 1 (default): discrete observations (Embedding -> Flatten -> Linear, representations.py:47-51) use the kernel that stages
+ * the transposed Linear weight and the table in shared memory; 0: the generic per-channel kernel (same arithmetic). */
+int dtqn_set_embed_disc_fast(int32_t on);
 /* debug: device buffer of >= 256 int64 that receives clock64 phase stamps of CTA 0 of the fused acting kernel (NULL: off). */
 int dtqn_set_act_fused_timeline(void* device_buf);
 /* 1 if a tcgen05 kernel ever timed out on an mbarrier (synchronises). */
