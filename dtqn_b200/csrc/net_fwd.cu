@@ -142,61 +142,67 @@ embed_disc_kernel(GroupPtrs P, GroupSrc S, int O, int E, int vocab, long long em
     const int g = blockIdx.z, tid = threadIdx.x;
     const float* p = P.p[g];
     const long long Tg = (long long)n_seq * L;
-    const long long t0 = (long long)blockIdx.x * ED_TOK;
-    for (int e = tid; e < D * KI; e += 256) {                  // coalesced read of W[c][k], transposed store
-        const int c = e / KI, k = e % KI;
+    for (int c = tid / KI, k = tid % KI, e = tid; e < D * KI; e += 256) {   // coalesced read of W[c][k], transposed store
         sWT[k * LDW + c] = __ldg(p + emb_w + e);
+        k += 256; while (k >= KI) { k -= KI; ++c; }
     }
     for (int e = tid; e < D; e += 256) sB[e] = __ldg(p + emb_b + e);
     for (int e = tid; e < vocab * E; e += 256) sTab[e] = __ldg(p + emb_table + e);
-    __syncthreads();
-    for (int e = tid; e < ED_TOK * O; e += 256) {              // one (token, feature) pair per thread: gather E table values
-        const int tl = e / O, k = e % O;
-        const long long t = t0 + tl;
-        if (t < Tg) {
-            const int i = (int)(t / L), j = (int)(t % L);
-            const dtqn_obs_src& s = S.s[g];
-            int row = j; bool valid = true;
-            if (s.timestep) {
-                const int ts = s.timestep[i];
-                const int n = min(s.ring_len, ts + 1);
-                valid = j < n;
-                row = valid ? (ts + 1 - n + j) % s.ring_len : 0;
-            }
-            const float ov = valid ? __ldg(s.obs + (long long)i * s.seq_stride + (long long)row * O + k) : obs_mask;
-            int tok = (int)ov;
-            tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
-            for (int q = 0; q < E; ++q) sE[tl * KI + k * E + q] = sTab[tok * E + q];
-        }
-    }
-    __syncthreads();
     constexpr int TPT = D / 16;                               // threads per token
     constexpr int TPP = 256 / TPT;                            // tokens per pass
-    const int c0 = (tid % TPT) * 16;
-    for (int tl = tid / TPT; tl < ED_TOK; tl += TPP) {
-        const long long t = t0 + tl;
-        if (t >= Tg) break;
-        const int j = (int)(t % L);
-        float acc[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) acc[q] = sB[c0 + q];
-        const float* er = sE + tl * KI;
-        for (int kk = 0; kk < KI; ++kk) {
-            const float tv = er[kk];
-            const float* w = sWT + kk * LDW + c0;
-#pragma unroll
-            for (int q = 0; q < 16; q += 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(w + q);
-                acc[q] = fmaf(tv, w4.x, acc[q]); acc[q + 1] = fmaf(tv, w4.y, acc[q + 1]);
-                acc[q + 2] = fmaf(tv, w4.z, acc[q + 2]); acc[q + 3] = fmaf(tv, w4.w, acc[q + 3]);
+    // channel quads of this thread: c0 + q * CQ (q = 0..3) -- the TPT threads of a token read CONTIGUOUS float4s of a weight
+    // row (conflict-free; a 16-channel block per thread would put every second thread on the same banks)
+    constexpr int CQ = TPT * 4;
+    const int c0 = (tid % TPT) * 4;
+    const dtqn_obs_src s = S.s[g];
+    // persistent over token chunks: the weight image is staged once per CTA
+    for (long long t0 = (long long)blockIdx.x * ED_TOK; t0 < Tg; t0 += (long long)gridDim.x * ED_TOK) {
+        __syncthreads();                                      // staging done / previous chunk's rows consumed
+        for (int e = tid; e < ED_TOK * O; e += 256) {          // one (token, feature) pair per thread: gather E table values
+            const int tl = e / O, k = e % O;
+            const long long t = t0 + tl;
+            if (t < Tg) {
+                const int i = (int)(t / L), j = (int)(t % L);
+                int row = j; bool valid = true;
+                if (s.timestep) {
+                    const int ts = s.timestep[i];
+                    const int n = min(s.ring_len, ts + 1);
+                    valid = j < n;
+                    row = valid ? (ts + 1 - n + j) % s.ring_len : 0;
+                }
+                const float ov = valid ? __ldg(s.obs + (long long)i * s.seq_stride + (long long)row * O + k) : obs_mask;
+                int tok = (int)ov;
+                tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+                for (int q = 0; q < E; ++q) sE[tl * KI + k * E + q] = sTab[tok * E + q];
             }
         }
-        const float* pp = p + pos_off + (long long)j * D + c0;
-        float* out = x0 + ((long long)g * Tg + t) * D + c0;
+        __syncthreads();
+        for (int tl = tid / TPT; tl < ED_TOK; tl += TPP) {
+            const long long t = t0 + tl;
+            if (t >= Tg) break;
+            const int j = (int)(t % L);
+            float acc[16];
 #pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-            const float4 pv = __ldg(reinterpret_cast<const float4*>(pp + q));
-            *reinterpret_cast<float4*>(out + q) = make_float4(acc[q] + pv.x, acc[q + 1] + pv.y, acc[q + 2] + pv.z, acc[q + 3] + pv.w);
+            for (int q = 0; q < 16; ++q) acc[q] = sB[c0 + (q >> 2) * CQ + (q & 3)];
+            const float* er = sE + tl * KI;
+#pragma unroll 4
+            for (int kk = 0; kk < KI; ++kk) {
+                const float tv = er[kk];
+                const float* w = sWT + kk * LDW + c0;
+#pragma unroll
+                for (int q = 0; q < 16; q += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + (q >> 2) * CQ);
+                    acc[q] = fmaf(tv, w4.x, acc[q]); acc[q + 1] = fmaf(tv, w4.y, acc[q + 1]);
+                    acc[q + 2] = fmaf(tv, w4.z, acc[q + 2]); acc[q + 3] = fmaf(tv, w4.w, acc[q + 3]);
+                }
+            }
+            const float* pp = p + pos_off + (long long)j * D + c0;
+            float* out = x0 + ((long long)g * Tg + t) * D + c0;
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(pp + (q >> 2) * CQ));
+                *reinterpret_cast<float4*>(out + (q >> 2) * CQ) = make_float4(acc[q] + pv.x, acc[q + 1] + pv.y, acc[q + 2] + pv.z, acc[q + 3] + pv.w);
+            }
         }
     }
 }
@@ -724,7 +730,8 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         } else if (cfg->discrete && g_embed_disc_fast && lay.k_in <= 128) {
             const int KI = lay.k_in;
             const size_t smem = sizeof(float) * ((size_t)KI * (d + 4) + d + ((cfg->vocab * cfg->embed_per_obs + 3) & ~3) + (size_t)ED_TOK * KI);
-            dim3 grid(dtqn_cdiv(Tg, ED_TOK), 1, G);
+            long long chunks = dtqn_cdiv(Tg, ED_TOK);
+            dim3 grid((unsigned)(chunks < 3 * 148 ? chunks : 3 * 148), 1, G);   // persistent: <= 3 CTAs per SM, W staged once per CTA
             const float mask = (float)(cfg->vocab - 1);
             cudaError_t ae = cudaSuccess;
             if (d == 64) {
