@@ -20,6 +20,9 @@
 //   warp 17     lane 0 streams the weight image (240 KB per tile, L2-resident) through a 64 KB shared-memory buffer with
 //               cp.async.bulk (TMA) + mbarrier complete_tx, each block as soon as the MMAs reading its slots have retired
 // TMEM (512 columns): [0,256) in_proj / ffn.0 accumulators (+ x0 stash), [256,320) out_proj / ffn.2, [320,512) final-layer in_proj.
+// Tiles are serial inside a CTA except for one overlap: as soon as the final-layer in_proj has retired, the NEXT tile's
+// embedding is published and its in_proj MMAs (own TMEM region) run under this tile's last-row attention.
+// Measured: profiles/README.md (241 us for 4096 x 50 tokens, phase timeline, ncu --set full).
 #include "net.cuh"
 #include "prof.cuh"
 #include "linear_tc.cuh"
@@ -60,7 +63,7 @@ static_assert(AF_SMEM <= 227 * 1024, "fused acting forward: shared memory budget
 struct ActFusedArgs {
     GroupPtrs P;
     GroupSrc S;
-    const uint8_t* img[DTQN_MAX_GROUPS];           // 15-chunk weight image of each group's network
+    const uint8_t* img[DTQN_MAX_GROUPS];           // 240 KB weight image of each group's network (IMG_* blocks)
     long long emb_w, emb_b, pos;
     LayerOff l0, l1;
     int O, n_seq, L;
