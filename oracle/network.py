@@ -1,8 +1,8 @@
 """CPU oracle restatement of the DTQN Q-network forward in plain torch fp32 (test infrastructure only).
 
 Follows dtqn/networks/dtqn.py:158-218, transformer.py:63-78 (post-LN block, ReLU on the sub-layer outputs,
-causal additive -inf mask :49-53), representations.py:17-23,25-52,64-75, position_encodings.py:19-43,
-gates.py:40-41 (ResGate) and utils/torch_utils.py:4-15 (init).  ``nn.MultiheadAttention`` is restated in closed
+causal additive -inf mask :49-53; :86-101 identity-map reordering), representations.py:17-23,25-52,64-75,146-155,
+position_encodings.py:19-43, gates.py:5-41 (ResGate, GRUGate) and utils/torch_utils.py:4-15 (init).  ``nn.MultiheadAttention`` is restated in closed
 form: qkv = x W_in^T + b_in with rows [0:d]=Q, [d:2d]=K, [2d:3d]=V; heads are contiguous d/H
 slices; S = (Q/sqrt(hd)) K^T + mask; P = softmax(S); O = concat_h(P V) W_out^T + b_out; LayerNorm eps 1e-5.
 The functions take a reference-compatible ``state_dict`` (key names of SURVEY.md section 8 a11) so the same weights
@@ -81,8 +81,8 @@ def embed(sd, obss):
     return obss.float() @ sd["obs_embedding.observation_embedding.weight"].T + sd["obs_embedding.observation_embedding.bias"]
 
 
-def layer_forward(sd, prefix, x, num_heads):
-    """transformer.py:63-78."""
+def attention(sd, prefix, x, num_heads):
+    """nn.MultiheadAttention(x, x, x, attn_mask=causal) in closed form (transformer.py:64-70)."""
     B, L, d = x.shape
     hd = d // num_heads
     qkv = x @ sd[prefix + "attention.in_proj_weight"].T + sd[prefix + "attention.in_proj_bias"]
@@ -92,20 +92,50 @@ def layer_forward(sd, prefix, x, num_heads):
     v = v.view(B, L, num_heads, hd).transpose(1, 2)
     s = q @ k.transpose(-1, -2) + sd[prefix + "attn_mask"][:L, :L]
     o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, L, d)
-    a = o @ sd[prefix + "attention.out_proj.weight"].T + sd[prefix + "attention.out_proj.bias"]
-    x = F.layer_norm(x + torch.relu(a), (d,), sd[prefix + "layernorm1.weight"], sd[prefix + "layernorm1.bias"], 1e-5)
-    h = torch.relu(x @ sd[prefix + "ffn.0.weight"].T + sd[prefix + "ffn.0.bias"])
-    f = h @ sd[prefix + "ffn.2.weight"].T + sd[prefix + "ffn.2.bias"]
-    return F.layer_norm(x + torch.relu(f), (d,), sd[prefix + "layernorm2.weight"], sd[prefix + "layernorm2.bias"], 1e-5)
+    return o @ sd[prefix + "attention.out_proj.weight"].T + sd[prefix + "attention.out_proj.bias"]
 
 
-def forward(sd, obss, num_heads):
-    """dtqn.py:158-218 with action_dim = 0, bag_size = 0, dropout = 0 (run.py defaults :98-103,151-153,173-175)."""
+def gate(sd, prefix, x, y):
+    """gates.py: ResGate (:40-41) unless the layer carries GRUGate parameters (:5-31; the SAME two gate modules are shared by
+    every layer, dtqn.py:107-131, so the state_dict repeats them under each layer's prefix)."""
+    if prefix + "w_r.weight" not in sd:
+        return x + y
+    lin = lambda name, t: t @ sd[prefix + name + ".weight"].T
+    z = torch.sigmoid(lin("w_z", y) + sd[prefix + "w_z.bias"] + lin("u_z", x))
+    r = torch.sigmoid(lin("w_r", y) + lin("u_r", x))
+    h = torch.tanh(lin("w_g", y) + lin("u_g", r * x))
+    return (1.0 - z) * x + z * h
+
+
+def layer_forward(sd, prefix, x, num_heads, identity=False):
+    """transformer.py:63-78 (post-LN block) or :86-101 (TransformerIdentityLayer, the GTrXL identity-map reordering)."""
+    d = x.shape[-1]
+    ln1 = lambda t: F.layer_norm(t, (d,), sd[prefix + "layernorm1.weight"], sd[prefix + "layernorm1.bias"], 1e-5)
+    ln2 = lambda t: F.layer_norm(t, (d,), sd[prefix + "layernorm2.weight"], sd[prefix + "layernorm2.bias"], 1e-5)
+    ffn = lambda t: torch.relu(t @ sd[prefix + "ffn.0.weight"].T + sd[prefix + "ffn.0.bias"]) @ sd[prefix + "ffn.2.weight"].T + sd[prefix + "ffn.2.bias"]
+    if identity:
+        x = gate(sd, prefix + "attn_gate.", x, torch.relu(attention(sd, prefix, ln1(x), num_heads)))
+        return gate(sd, prefix + "mlp_gate.", x, torch.relu(ffn(ln2(x))))
+    x = ln1(gate(sd, prefix + "attn_gate.", x, torch.relu(attention(sd, prefix, x, num_heads))))
+    return ln2(gate(sd, prefix + "mlp_gate.", x, torch.relu(ffn(x))))
+
+
+def forward(sd, obss, num_heads, actions=None, identity=False):
+    """dtqn.py:158-218 with bag_size = 0, dropout = 0.  Defaults (run.py :98-103,151-153,173-175): action_dim = 0 (no
+    ``action_embedding.*`` keys), gate = res, identity = False.  With an action embedding (dtqn.py:184-192) the previous
+    action's embedding is concatenated IN FRONT of the observation embedding; position 0 gets zeros."""
     L = obss.shape[1]
     assert L <= sd["position_embedding.position_encoding"].shape[1], "Cannot forward, history is longer than expected."
-    x = embed(sd, obss) + sd["position_embedding.position_encoding"][:, :L, :]
+    x = embed(sd, obss)
+    if "action_embedding.embedding.0.weight" in sd:
+        a = sd["action_embedding.embedding.0.weight"][actions.long()].flatten(start_dim=-2)       # [B, L, action_dim]
+        if L > 1:
+            a = torch.roll(a, 1, 1)
+            a = torch.cat([torch.zeros_like(a[:, :1]), a[:, 1:]], dim=1)
+        x = torch.cat([a, x], dim=-1)
+    x = x + sd["position_embedding.position_encoding"][:, :L, :]
     for i in range(num_layers_of(sd)):
-        x = layer_forward(sd, f"transformer_layers.{i}.", x, num_heads)
+        x = layer_forward(sd, f"transformer_layers.{i}.", x, num_heads, identity)
     h = torch.relu(x @ sd["ffn.0.weight"].T + sd["ffn.0.bias"])
     return h @ sd["ffn.2.weight"].T + sd["ffn.2.bias"]
 

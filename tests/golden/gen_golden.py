@@ -227,7 +227,49 @@ def gen_acting(env_id, inner_embed, context, steps, tag):
     print("wrote", f"acting_{tag}.npz")
 
 
+ABLATIONS = {                # name -> DTQN kwargs (run.py flags --identity / --gate gru / --a-embed 8 and their combination)
+    "identity": dict(identity=True, gate="res", action_dim=0),
+    "gru": dict(identity=False, gate="gru", action_dim=0),
+    "aembed": dict(identity=False, gate="res", action_dim=8),
+    "gtrxl_aembed": dict(identity=True, gate="gru", action_dim=8),
+}
+
+
+def gen_ablations():
+    """Reference DTQN built directly with the ablation flags: forward Q for L = 1, 9 and the
+    gradient of sum(Q^2) w.r.t. every trainable parameter -> pins the oracle's identity / GRU-gate / action-embedding
+    restatement (the CUDA kernels for these flags follow the oracle)."""
+    from dtqn.networks.dtqn import DTQN
+    out = {}
+    O, A, d, ctx, H = 3, 3, 32, 12, 4
+    for name, kw in ABLATIONS.items():
+        gen = torch.Generator().manual_seed(21)
+        torch.manual_seed(3)
+        net = DTQN(O, A, 8, kw["action_dim"], d, H, 2, ctx, dropout=0.0, gate=kw["gate"], identity=kw["identity"],
+                   pos="learned", discrete=False)
+        perturb(net, gen)
+        out.update(sd_np(net.state_dict(), f"{name}/sd/"))
+        for L in (1, 9):
+            x = torch.empty(4, L, O).uniform_(-1.1, 1.1, generator=gen)
+            a = torch.randint(0, A, (4, L, 1), generator=gen)
+            q = net(x, a) if kw["action_dim"] else net(x)
+            out[f"{name}/L{L}/obss"], out[f"{name}/L{L}/actions"] = x.numpy(), a.numpy()
+            out[f"{name}/L{L}/q"] = q.detach().numpy().copy()
+            if L == 9:
+                net.zero_grad()
+                (q ** 2).sum().backward()
+                for n, p_ in net.named_parameters():
+                    if p_.grad is not None:
+                        out[f"{name}/grad/{n}"] = p_.grad.detach().numpy().copy()
+    out["meta"] = np.array([d, 2, ctx, H])
+    np.savez_compressed(os.path.join(HERE, "forward_ablations.npz"), **out)
+    print("wrote forward_ablations.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ablations":
+        gen_ablations()
+        sys.exit(0)
     np.savez_compressed(os.path.join(HERE, "env_carflag.npz"), **gen_env("DiscreteCarFlag-v0", 24, 700))
     np.savez_compressed(os.path.join(HERE, "env_memory.npz"), **gen_env("Memory-5-v0", 24, 400))
     print("wrote env fixtures")
@@ -236,3 +278,4 @@ if __name__ == "__main__":
     gen_train("DiscreteCarFlag-v0", 64, 2, 50, 32, 12000, 3, "carflag")
     gen_train("Memory-5-v0", 128, 1, 50, 8, 1500, 2, "memory")
     gen_acting("DiscreteCarFlag-v0", 64, 50, 260, "carflag")
+    gen_ablations()

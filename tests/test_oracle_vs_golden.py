@@ -144,3 +144,47 @@ def test_acting_context_and_greedy_q(golden_dir):
         with torch.no_grad():
             q = onet.forward(sd, torch.from_numpy(win).float()[None], heads)[0, -1].numpy()
         assert np.abs(q - z["greedy_q"][t]).max() < 5e-6
+
+
+@pytest.mark.parametrize("name", ["identity", "gru", "aembed", "gtrxl_aembed"])
+def test_oracle_ablation_variants_match_reference(golden_dir, name):
+    """--identity (transformer.py:86-101), --gate gru (gates.py:5-31, shared across layers), --a-embed (dtqn.py:184-192):
+    the oracle's restatement against the reference module's Q values and autograd gradients."""
+    import torch
+    from oracle import network as onet
+    z = np.load(os.path.join(golden_dir, "forward_ablations.npz"))
+    d, layers, ctx, H = [int(v) for v in z["meta"]]
+    pre = f"{name}/sd/"
+    sd = {k[len(pre):]: torch.from_numpy(z[k]).clone() for k in z.files if k.startswith(pre)}
+    identity = name in ("identity", "gtrxl_aembed")
+    has_a = "action_embedding.embedding.0.weight" in sd
+    assert ("transformer_layers.0.attn_gate.w_r.weight" in sd) == (name in ("gru", "gtrxl_aembed"))
+    # shared gate modules: one leaf per distinct tensor, so autograd accumulates both layers' contributions like the reference
+    leaves = {}
+    for k in list(sd):
+        if k.endswith("attn_mask"):
+            continue
+        base = k.replace("transformer_layers.1.attn_gate", "transformer_layers.0.attn_gate").replace(
+            "transformer_layers.1.mlp_gate", "transformer_layers.0.mlp_gate")
+        if base != k:
+            assert torch.equal(sd[k], sd[base])
+            sd[k] = leaves.setdefault(base, sd[base].requires_grad_(True))
+        else:
+            sd[k] = leaves.setdefault(k, sd[k].requires_grad_(True))
+    for L in (1, 9):
+        x = torch.from_numpy(z[f"{name}/L{L}/obss"])
+        a = torch.from_numpy(z[f"{name}/L{L}/actions"])
+        q = onet.forward(sd, x, H, actions=a if has_a else None, identity=identity)
+        ref = z[f"{name}/L{L}/q"]
+        assert np.abs(q.detach().numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (name, L)
+        if L == 9:
+            (q ** 2).sum().backward()
+            n_checked = 0
+            for k in z.files:
+                if not k.startswith(f"{name}/grad/"):
+                    continue
+                key = k[len(f"{name}/grad/"):]
+                g, gr = leaves[key].grad.numpy(), z[k]
+                assert np.abs(g - gr).max() <= 1e-4 * max(np.abs(gr).max(), 1e-6), (name, key)
+                n_checked += 1
+            assert n_checked >= 30
