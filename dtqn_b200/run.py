@@ -5,8 +5,9 @@
 
 One "timestep" of the reference loop (run.py:290) is one lockstep iteration here: every env takes one step and the agent
 takes one gradient step, so ``--num-steps`` iterations collect ``num-steps x n-envs x world`` transitions.  New flag (no
-reference analogue): ``--n-envs`` lockstep environments per GPU.  Logging / wandb / rendering flags are accepted for
-command-line compatibility; losses and evaluation results are printed (rank 0) every ``--eval-frequency``.
+reference analogue): ``--n-envs`` lockstep environments per GPU.  Every ``--eval-frequency`` iterations rank 0 logs the
+reference's keys (run.py:303-325) through ``dtqn_b200.logging_utils`` -- ``<policy_path>_results.csv`` / ``_losses.csv`` with
+``--disable-wandb``, wandb otherwise -- and prints the ``--verbose`` line; ``--render`` is accepted and ignored.
 Checkpoint / resume follows run.py:452-499,337-352,526-529: the same ``policies/<project>/<env>/model=..._seed=N`` path
 prefix, ``_mini_checkpoint.pt`` / ``_checkpoint.pt`` / ``buffer_*.sav`` files (one set per rank, suffix ``_rank<r>`` when
 world > 1), written when ``--time-limit`` expires and read back on the next launch.
@@ -103,7 +104,8 @@ def run_experiment(args):
             if world > 1:
                 dist.destroy_process_group()
             return tr
-        _, mean_success_rate, mean_reward, mean_episode_length = tr.load_checkpoint(ckpt)
+        wandb_id, mean_success_rate, mean_reward, mean_episode_length = tr.load_checkpoint(ckpt)
+        wandb_kwargs = {"resume": "must", "id": wandb_id} if wandb_id else {"resume": None}            # run.py:490
     else:
         # prepopulate 50 000 transitions (run.py:495) with the random policy, and at least until a batch can be sampled
         steps = max(1, 50_000 // args.n_envs)
@@ -111,6 +113,11 @@ def run_experiment(args):
         while not tr.agent.replay_buffer.can_sample(args.batch):
             tr.prepopulate(16)
         mean_success_rate, mean_reward, mean_episode_length = RunningAverage(10), RunningAverage(10), RunningAverage(10)
+        wandb_kwargs = {"resume": None}                                                           # run.py:493
+    logger = None
+    if rank == 0:
+        from dtqn_b200 import logging_utils
+        logger = logging_utils.get_logger(policy_path, args, wandb_kwargs)                       # run.py:501
     if not args.no_graph:
         tr.enable_graphs()
     start = time.time()
@@ -120,11 +127,14 @@ def run_experiment(args):
             sr, ret, length = tr.evaluate(max(1, args.eval_episodes // 10))
             mean_success_rate.add(sr); mean_reward.add(ret); mean_episode_length.add(length)     # run.py:316-318
             if rank == 0:
-                a = tr.agent
-                print(f"[{timestep}] env-steps {timestep * args.n_envs * world}  TD {a.td_errors.mean():.5f}  "
-                      f"grad-norm {a.grad_norms.mean():.4f}  Q {a.qvalue_mean.mean():.4f}  "
-                      f"{args.envs[0]}/SuccessRate {sr:.3f}  Return {ret:.3f}  EpisodeLength {length:.1f}  "
-                      f"hours {(time.time() - start) / 3600:.3f}", flush=True)
+                hours = (time.time() - start) / 3600
+                log_vals = logging_utils.loss_log_values(tr.agent, hours)                        # run.py:303-313
+                log_vals.update({f"{args.envs[0]}/SuccessRate": sr, f"{args.envs[0]}/Return": ret,
+                                 f"{args.envs[0]}/EpisodeLength": length})                       # run.py:318-324
+                logger.log(log_vals, step=timestep)
+                if args.verbose:                                                                 # run.py:332-335
+                    print(f"[ {logging_utils.timestamp()} ] Training Steps: {timestep}, Env: {args.envs[0]}, Success Rate: "
+                          f"{sr:.2f}, Return: {ret:.2f}, Episode Length: {length:.2f}, Hours: {hours:.2f}", flush=True)
         if args.save_policy and timestep % 50_000 == 0 and rank == 0:                           # run.py:337-338
             torch.save(tr.agent.policy_network.state_dict(), policy_path)
         stop = False
@@ -136,10 +146,11 @@ def run_experiment(args):
                 stop = bool(flag.item())
         if stop:
             print(f"Reached time limit. Saving checkpoint with {tr.agent.num_train_steps} steps completed.")
-            tr.save_checkpoint(ckpt, None, mean_success_rate, mean_reward, mean_episode_length)
+            run_id = getattr(getattr(logger, "run", None), "id", None)                           # wandb.run.id (run.py:347)
+            tr.save_checkpoint(ckpt, run_id, mean_success_rate, mean_reward, mean_episode_length)
             break
     else:
-        tr.agent.save_mini_checkpoint(ckpt, None)                                               # run.py:526-529
+        tr.agent.save_mini_checkpoint(ckpt, getattr(getattr(logger, "run", None), "id", None))                                               # run.py:526-529
     if world > 1:
         dist.destroy_process_group()
     return tr
