@@ -86,3 +86,73 @@ def test_run_flags_match_reference_defaults():
     ref["envs"] = [ref["envs"]] if isinstance(ref["envs"], str) else ref["envs"]
     differing = {k: (ref[k], mine[k]) for k in ref if ref[k] != mine[k]}
     assert not differing, differing
+
+
+def test_run_experiment_control_flow_with_a_stub_trainer(tmp_path, monkeypatch):
+    """run_experiment's host logic (prepopulate, eval cadence, logging keys, mini checkpoint, early exit on a finished run)
+    driven with a stub in place of the CUDA trainer: no kernel runs here, only the loop shape of run.py:246-353,452-529."""
+    import torch
+    import dtqn_b200.runner as runner
+    from dtqn_b200.checkpoint import RunningAverage
+    from dtqn_b200 import run as b200_run
+
+    class FakeRB:
+        def can_sample(self, n):
+            return True
+
+    class FakeAgent:
+        def __init__(self):
+            self.policy_network = torch.nn.Linear(3, 3)
+            self.replay_buffer = FakeRB()
+            self.num_train_steps = 0
+            for nm in ("td_errors", "grad_norms", "qvalue_max", "qvalue_mean", "qvalue_min", "target_max", "target_mean", "target_min"):
+                ra = RunningAverage(100); ra.add(0.5); setattr(self, nm, ra)
+            self.mini = None
+
+        def save_mini_checkpoint(self, path, wandb_id):
+            torch.save({"step": self.num_train_steps, "wandb_id": wandb_id}, path + "_mini_checkpoint.pt")
+
+        def load_mini_checkpoint(self, path):
+            return torch.load(path + "_mini_checkpoint.pt")
+
+    class FakeTrainer:
+        calls = []
+
+        def __init__(self, env_id, n_envs, **kw):
+            self.rank, self.world, self.agent, self.kw = 0, 1, FakeAgent(), kw
+            FakeTrainer.calls.append(("init", env_id, n_envs))
+
+        def prepopulate(self, steps):
+            FakeTrainer.calls.append(("prepopulate", steps))
+
+        def enable_graphs(self):
+            FakeTrainer.calls.append(("graphs",))
+
+        def train_iteration(self):
+            self.agent.num_train_steps += 1
+
+        def evaluate(self, episodes):
+            FakeTrainer.calls.append(("evaluate", episodes))
+            return 0.75, 0.5, 40.0
+
+    monkeypatch.setattr(runner, "BatchedTrainer", FakeTrainer)
+    monkeypatch.chdir(tmp_path)
+    args = b200_run.get_args(["--envs", "DiscreteCarFlag-v0", "--in-embed", "64", "--n-envs", "1000", "--num-steps", "25",
+                              "--eval-frequency", "10", "--disable-wandb", "--device", "cpu", "--verbose"])
+    tr = b200_run.run_experiment(args)
+    assert tr.agent.num_train_steps == 25
+    assert ("prepopulate", 50) in FakeTrainer.calls and ("graphs",) in FakeTrainer.calls          # 50 000 // 1000 lockstep steps
+    assert [c for c in FakeTrainer.calls if c[0] == "evaluate"] == [("evaluate", 1)] * 3          # timesteps 0, 10, 20
+    pol = tmp_path / "policies" / "DTQN-test" / "DiscreteCarFlag-v0"
+    files = sorted(os.listdir(pol))
+    prefix = [f for f in files if f.endswith("_results.csv")][0][: -len("_results.csv")]
+    assert prefix.startswith("model=DTQN_envs=DiscreteCarFlag-v0_obs_embed=8_a_embed=0_in_embed=64_context=50_heads=8_layers=2")
+    rows = open(pol / (prefix + "_results.csv")).read().splitlines()
+    assert rows[0].startswith("Hours,Step,DiscreteCarFlag-v0/SuccessRate") and [r.split(",")[1] for r in rows[1:]] == ["0", "10", "20"]
+    assert rows[1].split(",")[2:] == ["0.75", "40.0", "0.5"]
+    assert len(open(pol / (prefix + "_losses.csv")).read().splitlines()) == 4
+    assert torch.load(pol / (prefix + "_mini_checkpoint.pt"))["step"] == 25
+    # a second launch finds the finished run and exits without training (run.py:469-481)
+    n_calls = len(FakeTrainer.calls)
+    tr2 = b200_run.run_experiment(args)
+    assert tr2.agent.num_train_steps == 0 and not any(c[0] == "prepopulate" for c in FakeTrainer.calls[n_calls:])
