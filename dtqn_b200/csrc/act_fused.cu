@@ -548,6 +548,9 @@ act_fused_kernel(ActFusedArgs t) {
                 }
             }
             STAMP(i, 23);
+            // The next tile's in_proj has usually retired by now (it ran under this phase), so nothing else orders the next
+            // q|k|v dump -- which overwrites the staged tile -- after the slowest warp's last-row attention reads of it.
+            worker_bar();
         }
     } else if (warp == 16) {
         // =============================================== MMA issuer ===============================================
