@@ -135,43 +135,81 @@ def best_thread_count(lp):
         torch.set_num_threads(nt)
         lp.iteration()
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(6):
             lp.iteration()
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = nt, dt
-        if dt > 3.0:           # already hopeless at this thread count; larger counts only get worse
+        if dt > 6.0:           # already hopeless at this thread count; larger counts only get worse
             break
     torch.set_num_threads(best)
     return best
 
 
+REF_PREPOP = 50_000        # run.py:495
+REF_MIN_ITERS = 200        # >= 200 iterations per leg
+REF_EPS = 0.1              # exploration floor (run.py:420): the regime the 2M-step run spends ~90 % of its time in
+
+
+def time_reference(batch, min_iters=REF_MIN_ITERS, budget_s=12.0):
+    """The reference's CPU path on this host: the UNMODIFIED reference through oracle/ref_harness when /root/reference
+    exists (kind "reference"), else the oracle port of the same loop (kind "port").  Legs: (i)
+    run.prepopulate random-policy env-steps/s, (ii) run.step eps-greedy env-steps/s, (iii) agent.train() grad-steps/s,
+    (iv) the loop body (1 env-step + 1 grad-step), all at the best torch thread count, plus (iv) at 1 thread."""
+    import torch
+    from oracle import ref_loop
+    if ref_loop.available():
+        lp, kind = ref_loop.RealReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX,
+                                              batch=batch), "reference"
+    else:
+        from oracle.loop import ReferenceLoop
+        lp, kind = ReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX, batch=batch), "port"
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    lp.prepopulate(REF_PREPOP)
+    prepop_sps = REF_PREPOP / (time.perf_counter() - t0)
+    lp.set_epsilon(REF_EPS)
+
+    def leg(fn, n_min, budget):
+        for _ in range(5):
+            fn()
+        t0 = time.perf_counter(); n = 0
+        while n < n_min or time.perf_counter() - t0 < budget:
+            fn(); n += 1
+            if time.perf_counter() - t0 > 6 * budget + 5:
+                break
+        return n / (time.perf_counter() - t0), n
+
+    one_thread, n1 = leg(lp.iteration, 50, 2.0)
+    cores = best_thread_count(lp)
+    loop_ps, n_loop = leg(lp.iteration, min_iters, budget_s)
+    step_ps, _ = leg(lp.step_only, min_iters, 1.0)
+    train_ps, _ = leg(lp.train_only, min_iters, 2.0)
+    return {"value": loop_ps, "unit": "env-steps/s", "grad_steps_per_sec": loop_ps, "cores": cores,
+            "host_cores": os.cpu_count(), "kind": kind,
+            "sample": (f"{n_loop} iterations of the 1-env reference loop body (run.py:290-298: 1 eps-greedy env-step at eps={REF_EPS} + "
+                       f"1 grad-step, batch {batch}) after {REF_PREPOP} prepopulate steps, {cores} torch threads"),
+            "one_thread_value": one_thread, "one_thread_iterations": n1,
+            "legs": {"prepopulate_env_steps_per_sec_1thread": prepop_sps, "run_step_env_steps_per_sec": step_ps,
+                     "agent_train_grad_steps_per_sec": train_ps, "loop_iterations_per_sec": loop_ps}}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: the oracle port of the reference loop (1 env, batch 32) on all host cores; rank 0 only."""
+    """CPU arm: the reference's own loop (1 env, batch 32) on the host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
-    from oracle.loop import ReferenceLoop
-    lp = ReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX, batch=args.batch)
-    lp.prepopulate(8000)                      # enough completed episodes for can_sample(32); the reference uses 50k
-    cores = best_thread_count(lp)
-    for _ in range(max(3, args.warmup)):
-        lp.iteration()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lp.iteration()
-    dt = time.perf_counter() - t0
-    v = args.steps / dt
+    cpu = time_reference(args.batch, min_iters=max(REF_MIN_ITERS, args.steps), budget_s=15.0)
+    v = cpu["value"]
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "grad_steps_per_sec": v,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{ENV_ID}, DTQN ctx={CTX}, in-embed={EMBED}, 1 env, batch {args.batch}, reference CPU loop "
-                               "(oracle port of run.py:290-298: act + env.step + store + train per step)",
-                   "threads": cores, "host_cores": os.cpu_count()},
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} loop iterations (1 env-step + 1 grad-step each) after 8000 prepopulate steps"},
+                               "(run.py:290-298: act + env.step + store + train per step)",
+                   "threads": cpu["cores"], "host_cores": os.cpu_count(),
+                   "timed_iterations": "max(200, --steps) loop iterations after 50 000 prepopulate steps (run.py:495)"},
+        "cpu_baseline": cpu,
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,13 +245,39 @@ def main():
     # up to 200 steps, so ~250 lockstep steps = ~1M transitions per rank)
     tr.prepopulate(260)
     assert tr.agent.replay_buffer.can_sample(args.batch)
-    if use_graph:
-        tr.enable_graphs()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def replicas_identical(t):
+        """Parameters and both Adam moments bit-identical on every rank (min == max elementwise over ranks)."""
+        ok = True
+        for x in (t.agent.policy_network.flat, t.agent.exp_avg, t.agent.exp_avg_sq, t.agent.target_network.flat):
+            lo, hi = x.clone(), x.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ok = ok and bool(torch.equal(lo, hi)) and bool(torch.isfinite(x).all())
+        return ok
+
+    # ---- N > 1 self-check: the gradient collective of one real update against NCCL's allreduce of the same gradients ----
+    exchange_check = None
+    if world > 1:
+        agent, rb = tr.agent, tr.agent.replay_buffer
+        eps_i, starts_i = rb.draw_indices(agent.batch_size)
+        rb.gather_windows(eps_i, starts_i, out=agent._win)
+        agent.forward_backward(*agent._win[:4])
+        want = agent.grads.clone()
+        dist.all_reduce(want)                               # NCCL sum of the per-rank gradients
+        agent.reduce_and_step()
+        agent.finish_step()
+        torch.cuda.synchronize()
+        got = agent.exchange.reduced if agent.exchange is not None else agent.grads
+        exchange_check = {"p2p_vs_nccl_max_abs": float((got - want).abs().max().item()),
+                          "grad_max_abs": float(want.abs().max().item()),
+                          "replicas_identical_after_first_update": replicas_identical(tr)}
+    if use_graph:
+        tr.enable_graphs()
 
     W = max(3, args.warmup)
     for _ in range(W):
@@ -236,6 +300,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms = float(ms.item())
     tr.agent.check_finite()
+    replicas_ok = replicas_identical(tr) if world > 1 else None
     env_sps = N * world * args.steps / (ms / 1e3)
     grad_sps = args.steps / (ms / 1e3)
 
@@ -391,21 +456,39 @@ def main():
                      "random_policy_env_steps_per_sec": N * 1e3 / ms_env, "env_step_plus_roll_us": 1e3 * ms_env,
                      "env_step_GBps_algorithmic_55B": 55.0 * N / (ms_env * 1e-3) / 1e9}
 
+    # ---- N > 1: the same loop with the NCCL allreduce as the gradient collective, timed beside the fused exchange ----
+    nccl_arm = None
+    if world > 1 and tr.allreduce == "p2p-fused":
+        os.environ["DTQN_B200_ALLREDUCE"] = "nccl"
+        tr2 = BatchedTrainer(ENV_ID, N, seed=1, device=dev, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX,
+                             batch=args.batch)
+        os.environ.pop("DTQN_B200_ALLREDUCE", None)
+        assert tr2.allreduce == "nccl"
+        tr2.prepopulate(260)
+        if use_graph:
+            tr2.enable_graphs()
+        for _ in range(W):
+            tr2.train_iteration()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            tr2.train_iteration()
+        a1.record()
+        barrier()
+        ms2 = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        tr2.agent.check_finite()
+        nccl_arm = {"ms_per_step": float(ms2.item()) / args.steps,
+                    "env_steps_per_sec": N * world * args.steps / (float(ms2.item()) / 1e3),
+                    "replicas_identical": replicas_identical(tr2),
+                    "note": "same loop, DTQN_B200_ALLREDUCE=nccl: torch.distributed.all_reduce of the flat gradient (outside the CUDA "
+                            "graph) + sqnorm + clip/Adam kernels"}
+        del tr2
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.loop import ReferenceLoop
-        lp = ReferenceLoop(ENV_ID, seed=1, inner_embed=EMBED, heads=HEADS, layers=LAYERS, context=CTX, batch=args.batch)
-        lp.prepopulate(8000)
-        cores = best_thread_count(lp)
-        for _ in range(5):
-            lp.iteration()
-        t0 = time.perf_counter(); n = 0
-        while time.perf_counter() - t0 < 12.0:
-            lp.iteration(); n += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": "env-steps/s", "grad_steps_per_sec": n / dt, "cores": cores,
-               "host_cores": os.cpu_count(), "kind": "port",
-               "sample": f"{n} iterations of the 1-env reference loop (1 env-step + 1 grad-step, batch {args.batch}) in {dt:.1f} s"}
+        cpu = time_reference(args.batch)
 
     if rank == 0:
         line = {
@@ -427,11 +510,13 @@ def main():
                                            ("agent.q_last_batched -> host eps-greedy -> BatchedEnv.step(host actions) -> "
                                             "host obs/reward/done -> agent.train -> host loss")},
             "gpu_launches": launches,
+            "replicas_identical": replicas_ok, "exchange_check": exchange_check, "nccl_arm": nccl_arm,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "breakdown": breakdown,
             "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,
         }
         _emit(line)
     if world > 1:
+        assert replicas_ok, "data-parallel replicas diverged (parameters / Adam moments differ between ranks)"
         dist.destroy_process_group()
 
 

@@ -20,10 +20,10 @@ _p = C.c_void_p
 
 class EnvStruct(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_envs", C.c_int32), ("obs_dim", C.c_int32), ("num_actions", C.c_int32),
-                ("max_episode_steps", C.c_int32), ("_pad", C.c_int32),
+                ("max_episode_steps", C.c_int32), ("stat_episodes_per_env", C.c_int32),
                 ("rng", _p), ("rng_buf", _p), ("arng", _p), ("arng_buf", _p),
                 ("pos", _p), ("vel", _p), ("heaven", _p), ("cards", _p), ("shown", _p), ("cur", _p),
-                ("elapsed", _p), ("done_flag", _p), ("block_counts", _p), ("ep_stats", _p), ("ep_return", _p)]
+                ("elapsed", _p), ("done_flag", _p), ("block_counts", _p), ("ep_stats", _p), ("ep_return", _p), ("env_acc", _p)]
 
 
 class ReplayStruct(C.Structure):
@@ -39,7 +39,7 @@ class ContextStruct(C.Structure):
 
 
 class StepIO(C.Structure):
-    _fields_ = [("action_mode", C.c_int32), ("epsilon", C.c_float), ("actions", _p), ("q_last", _p),
+    _fields_ = [("action_mode", C.c_int32), ("_pad", C.c_int32), ("epsilon", C.c_double), ("actions", _p), ("q_last", _p),
                 ("obs_out", _p), ("reward_out", _p), ("done_out", _p), ("truncated_out", _p), ("success_out", _p),
                 ("epsilon_dev", _p)]
 
@@ -60,6 +60,7 @@ def _load():
         "dtqn_env_step": [C.POINTER(EnvStruct), C.POINTER(ReplayStruct), C.POINTER(ContextStruct), C.POINTER(StepIO), _p],
         "dtqn_replay_sample_indices": [C.POINTER(ReplayStruct), C.c_int32, C.c_uint64, C.c_uint64, _p, _p, _p, _p],
         "dtqn_replay_gather": [C.POINTER(ReplayStruct), C.c_int32, _p, _p, _p, _p, _p, _p, _p, _p],
+        "dtqn_eps_anneal": [_p, _p, _p],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -176,7 +176,7 @@ class DtqnAgent:
         """Q of the last context position of every env ([n_envs, A]) from the device context ring."""
         cx, net = self.context, self.policy_network
         src = ObsSrc(obs=cx.obs.data_ptr(), seq_stride=cx.max_length * cx.env_obs_length,
-                     timestep=cx.timestep_t.data_ptr(), ring_len=cx.max_length, _pad=0)
+                     timestep=cx.timestep_t.data_ptr(), ring_len=cx.max_length, obs_mask=cx.obs_mask)
         forward_groups(net, [net], [src], self.n_envs, self.context_len, q_mode=1, save=0, q_out=self._q_last)
         return self._q_last
 
@@ -197,8 +197,8 @@ class DtqnAgent:
         net, tgt = self.policy_network, self.target_network
         B, L, O = obs_win.shape[0], self.context_len, self.env_obs_length
         stride = (L + 1) * O
-        s_obs = ObsSrc(obs=obs_win.data_ptr(), seq_stride=stride, timestep=None, ring_len=0, _pad=0)
-        s_next = ObsSrc(obs=obs_win.data_ptr() + 4 * O, seq_stride=stride, timestep=None, ring_len=0, _pad=0)
+        s_obs = ObsSrc(obs=obs_win.data_ptr(), seq_stride=stride, timestep=None, ring_len=0, obs_mask=float(self.obs_mask))
+        s_next = ObsSrc(obs=obs_win.data_ptr() + 4 * O, seq_stride=stride, timestep=None, ring_len=0, obs_mask=float(self.obs_mask))
         ws = forward_groups(net, [net, net, tgt], [s_obs, s_next, s_next], B, L, q_mode=0, save=1,
                             q_out=self._q_all)
         st = _lib.stream_ptr()

@@ -16,6 +16,7 @@ The pure functions (``adam_state_dict`` / ``load_adam_state_dict`` / ``running_a
 and are covered by the CPU tests; ``save_agent`` / ``load_agent`` / ``save_trainer`` / ``load_trainer`` move device
 tensors through host memory (plumbing, never on the hot path).
 """
+import pickle
 import random
 from typing import Dict, Iterable, Optional, Tuple
 
@@ -52,6 +53,43 @@ class RunningAverage:
         if isinstance(st, dict):
             return RunningAverage(st["size"], st["values"])
         return RunningAverage(getattr(st, "size", 10), list(getattr(st, "q", [])))     # a reference object, if unpickled
+
+
+# ---- reading checkpoint pickles ------------------------------------------------------------------------------------------
+class _RefRunningAverage:
+    """Stand-in for the reference's pickled ``utils.logging_utils.RunningAverage`` objects (dqn.py:245-258: size, q, sum):
+    the reference package is not importable where this library runs, and nothing of it needs to be."""
+    size, q, sum = 10, (), 0
+
+
+class _CheckpointPickle:
+    """``pickle_module`` for torch.load: resolves only the globals a DTQN checkpoint legitimately holds (torch tensors /
+    storages, numpy arrays and RNG state tuples, OrderedDict / deque, this module's classes) and maps the reference's
+    RunningAverage to a plain holder; any other global raises instead of being imported and executed."""
+    __name__ = "dtqn_b200.checkpoint._CheckpointPickle"
+    _ALLOWED_MODULES = ("torch", "numpy", "collections", "_codecs", "copyreg")
+    _ALLOWED_BUILTINS = {"set", "frozenset", "list", "dict", "tuple", "complex", "bytearray", "slice", "range", "int",
+                         "float", "bool", "str", "bytes", "getattr"}
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if (module, name) == ("utils.logging_utils", "RunningAverage"):
+                return _RefRunningAverage
+            if module == "dtqn_b200.checkpoint" and name in ("RunningAverage", "_RefRunningAverage"):
+                return globals()[name]
+            if module == "builtins" and name in _CheckpointPickle._ALLOWED_BUILTINS and name != "getattr":
+                return super().find_class(module, name)
+            if module.split(".")[0] in _CheckpointPickle._ALLOWED_MODULES:
+                return super().find_class(module, name)
+            raise pickle.UnpicklingError(f"checkpoint refers to {module}.{name}, which a DTQN checkpoint never holds")
+
+    @staticmethod
+    def load(f, **kw):
+        return _CheckpointPickle.Unpickler(f, **kw).load()
+
+
+def read_checkpoint_file(path: str) -> dict:
+    return torch.load(path, weights_only=False, map_location="cpu", pickle_module=_CheckpointPickle)
 
 
 # ---- torch.optim.Adam state_dict <-> flat moment buffers ------------------------------------------------------------------
@@ -112,7 +150,7 @@ def save_mini_checkpoint(agent, checkpoint_dir: str, wandb_id: Optional[str]) ->
 
 
 def load_mini_checkpoint(checkpoint_dir: str) -> dict:                                         # dqn.py:218-220
-    return torch.load(checkpoint_dir + "_mini_checkpoint.pt", weights_only=False)
+    return read_checkpoint_file(checkpoint_dir + "_mini_checkpoint.pt")
 
 
 def replay_arrays(rb) -> dict:
@@ -175,19 +213,32 @@ def save_agent(agent, checkpoint_dir: str, wandb_id: Optional[str], episode_succ
         joblib.dump(arrs[key], checkpoint_dir + f"buffer_{key}.sav")
 
 
-def load_agent(agent, checkpoint_dir: str):
-    """DqnAgent.load_checkpoint (dqn.py:281-327).  Returns (wandb_id, successes, rewards, lengths, epsilon, b200-extra)."""
+def load_agent(agent, checkpoint_dir: str, validate=None):
+    """DqnAgent.load_checkpoint (dqn.py:281-327).  Returns (wandb_id, successes, rewards, lengths, epsilon, b200-extra).
+    Everything is read and checked against this agent (buffer shapes, parameter shapes, ``validate(ck)`` of the caller)
+    BEFORE any of its state is overwritten, so a mismatched checkpoint raises and leaves the agent untouched."""
     import joblib
     from dtqn_b200.agents import RNG
-    ck = torch.load(checkpoint_dir + "_checkpoint.pt", weights_only=False, map_location="cpu")
+    ck = read_checkpoint_file(checkpoint_dir + "_checkpoint.pt")
     rb, net, dev = agent.replay_buffer, agent.policy_network, agent.device
-    agent.num_train_steps = int(ck["step"])
+    if validate is not None:
+        validate(ck)
+    arrays = []
     for dst, key, dt in ((rb.obss, "obss", torch.float32), (rb.actions, "actions", torch.uint8),
                          (rb.rewards, "rewards", torch.float32), (rb.dones, "dones", torch.uint8),
                          (rb.episode_lengths, "eplens", torch.int32)):
         arr = np.asarray(joblib.load(checkpoint_dir + f"buffer_{key}.sav"))
         if tuple(arr.shape) != tuple(dst.shape):
             raise ValueError(f"buffer_{key}.sav has shape {arr.shape}, this replay buffer expects {tuple(dst.shape)}")
+        arrays.append((dst, arr, dt))
+    want = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    for which in ("policy_net_state_dict", "target_net_state_dict"):
+        got = {k: tuple(v.shape) for k, v in ck[which].items()}
+        if got != want:
+            diff = sorted(set(got.items()) ^ set(want.items()))[:4]
+            raise ValueError(f"{which} does not match this network (first differences: {diff})")
+    agent.num_train_steps = int(ck["step"])
+    for dst, arr, dt in arrays:
         dst.copy_(torch.from_numpy(arr.astype(np.uint8) if arr.dtype == np.bool_ else arr).to(dt))
     net.load_state_dict(ck["policy_net_state_dict"])
     agent.target_network.load_state_dict(ck["target_net_state_dict"])
@@ -253,11 +304,14 @@ def save_trainer(tr, checkpoint_dir: str, wandb_id: Optional[str] = None, episod
 def load_trainer(tr, checkpoint_dir: str):
     """Restores agent + env streams + loop counters.  A captured CUDA graph is dropped (its device scalars were
     overwritten); call ``enable_graphs()`` again -- it performs the next loop iteration while it re-captures."""
-    tr.disable_graphs()
-    wandb_id, succ, rew, length, epsilon, b = load_agent(tr.agent, checkpoint_dir)
-    if b is not None and "env" in b:
-        if b["env_id"] != tr.env.env_id or int(b["n_envs"]) != tr.n_envs:
+    def validate(ck):
+        b = ck.get("b200")
+        if b is not None and "env" in b and (b["env_id"] != tr.env.env_id or int(b["n_envs"]) != tr.n_envs):
             raise ValueError(f"checkpoint holds {b['n_envs']} x {b['env_id']}, trainer runs {tr.n_envs} x {tr.env.env_id}")
+
+    wandb_id, succ, rew, length, epsilon, b = load_agent(tr.agent, checkpoint_dir, validate)
+    tr.disable_graphs()
+    if b is not None and "env" in b:
         for k, v in b["env"].items():
             getattr(tr.env, k).copy_(v)
         tr.iterations = int(b["iterations"])

@@ -674,7 +674,7 @@ int launch_act_fused(const dtqn_net_cfg& c, const NetLayout& lay, const GroupPtr
     t.P = P; t.S = S;
     for (int g = 0; g < G; ++g) t.img[g] = packed[g] + img_off;
     t.emb_w = lay.emb_w; t.emb_b = lay.emb_b; t.pos = lay.pos; t.l0 = lay.layer[0]; t.l1 = lay.layer[1];
-    t.O = c.obs_dim; t.n_seq = n_seq; t.L = L; t.obs_mask = -5.0f; t.xl = xl; t.ol = ol;
+    t.O = c.obs_dim; t.n_seq = n_seq; t.L = L; t.obs_mask = S.s[0].obs_mask; t.xl = xl; t.ol = ol;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(act_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM);

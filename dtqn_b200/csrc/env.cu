@@ -87,6 +87,7 @@ env_reset_all_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, int has_rb, in
     env_reset_one<KIND>(e, i, g, o);
     g.store(e.rng, e.rng_buf, e.n_envs, i);
     e.done_flag[i] = 0;
+    if (e.env_acc) { int* acc = e.env_acc + 4 * (size_t)i; acc[0] = acc[1] = acc[2] = acc[3] = 0; }
     if (has_rb) {                                                      // ReplayBuffer.store_obs (:88-92), slot = env index
         rb.env_slot[i] = i;
         rb.env_prev_len[i] = rb.episode_lengths[i];
@@ -110,7 +111,12 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
     const int i = blockIdx.x * ENV_THREADS + threadIdx.x;
     if (has_rb && i == 0) rb.counters[0] = rb.counters[1];            // publish last step's allocations
     int done = 0;
-    if (i < e.n_envs) {
+    // run.evaluate plays a fixed number of episodes per env (run.py:214-233): an env that has finished its
+    // stat_episodes_per_env-th episode is frozen -- no step, no RNG draw, no reset -- until the next dtqn_env_reset_all
+    bool frozen = false;
+    if (i < e.n_envs && e.env_acc && e.stat_episodes_per_env > 0) frozen = e.env_acc[4 * (size_t)i] >= e.stat_episodes_per_env;
+    if (i < e.n_envs && frozen) e.done_flag[i] = 0;
+    if (i < e.n_envs && !frozen) {
         // ---- action: run.py:394 (random), agents/dtqn.py:78-107 (eps-greedy), or supplied ----
         int a;
         const unsigned A = (unsigned)e.num_actions;
@@ -122,8 +128,8 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
                 a = (int)ag.bounded(A);
             } else {
                 double u = ag.next_double();
-                const float eps = io.epsilon_dev ? *io.epsilon_dev : io.epsilon;
-                if (u < (double)eps) {
+                const double eps = io.epsilon_dev ? *io.epsilon_dev : io.epsilon;   // f64 vs f64 like agents/dtqn.py:78
+                if (u < eps) {
                     a = (int)ag.bounded(A);
                 } else {                                               // torch.argmax: first maximal index
                     const float* q = io.q_last + (size_t)i * A;
@@ -228,11 +234,18 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
             ctx_write(cx, i, ts % cx.context_len, o, O);
         }
         if (done) {
+            if (e.env_acc) {
+                int* acc = e.env_acc + 4 * (size_t)i;
+                acc[0] += 1; acc[1] += ret; acc[2] += el; acc[3] += (success || ret > 0);
+                // the last counted episode is not followed by env.reset() / context_reset (the next evaluation starts with one)
+                if (e.stat_episodes_per_env > 0 && acc[0] >= e.stat_episodes_per_env) frozen = true;
+            }
             atomicAdd((unsigned long long*)&e.ep_stats[0], (unsigned long long)(long long)ret);
             atomicAdd((unsigned long long*)&e.ep_stats[1], (unsigned long long)el);
             atomicAdd((unsigned long long*)&e.ep_stats[2], (unsigned long long)(success || ret > 0));  // run.py:232
             atomicAdd((unsigned long long*)&e.ep_stats[3], 1ull);
         }
+        if (frozen) done = 0;                                          // nothing to roll
         e.done_flag[i] = (uint8_t)done;
     }
     const int cnt = __syncthreads_count(done);
@@ -332,9 +345,9 @@ int check_env(const dtqn_env* e, const dtqn_replay* rb, const dtqn_context* cx) 
 
 // LinearAnneal.anneal (utils/epsilon_anneal.py:33-34) kept on the device so a replayed CUDA graph needs no per-step host
 // write: emit the current value for this step, then val <- max(min, val - (val - min) / duration), in double like the host.
-__global__ void eps_anneal_kernel(double* state, float* eps_out) {
+__global__ void eps_anneal_kernel(double* state, double* eps_out) {
     const double val = state[0], lo = state[1], dur = state[2];
-    *eps_out = (float)val;
+    *eps_out = val;
     state[0] = fmax(lo, __dsub_rn(val, __ddiv_rn(__dsub_rn(val, lo), dur)));
 }
 
@@ -342,7 +355,7 @@ __global__ void eps_anneal_kernel(double* state, float* eps_out) {
 
 extern "C" int dtqn_version(void) { return DTQN_ABI_VERSION; }
 
-extern "C" int dtqn_eps_anneal(double* state, float* eps_out, void* stream) {
+extern "C" int dtqn_eps_anneal(double* state, double* eps_out, void* stream) {
     if (!state || !eps_out) return DTQN_E_ARG;
     eps_anneal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, eps_out);
     DTQN_LAUNCH_CHECK();

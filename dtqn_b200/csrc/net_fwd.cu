@@ -707,7 +707,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
                             cfg->n_layers >= 2 && L >= 3 && H * 32 <= 256;
     TcEmbed emb{};
     if (fuse_embed) {
-        emb.L = L; emb.O = cfg->obs_dim; emb.obs_mask = -5.0f; emb.w_off = lay.emb_w; emb.b_off = lay.emb_b; emb.pos_off = lay.pos;
+        emb.L = L; emb.O = cfg->obs_dim; emb.obs_mask = src[0].obs_mask; emb.w_off = lay.emb_w; emb.b_off = lay.emb_b; emb.pos_off = lay.pos;
         for (int g = 0; g < G; ++g) emb.src[g] = src[g];
     }
     auto linear = [&](const LinArgs& a, int epi, int tab_idx, int emb_mode = 0) -> int {
@@ -725,8 +725,8 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     if (!fuse_embed && !act_fused) {
         prof_begin(PROF_EMBED, st);
         if (!cfg->discrete && cfg->obs_dim <= 16) {
-            if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
-            else         embed_cont_kernel<128><<<dim3(dtqn_cdiv(Tg, 32), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, -5.0f, act.x0);
+            if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, src[0].obs_mask, act.x0);
+            else         embed_cont_kernel<128><<<dim3(dtqn_cdiv(Tg, 32), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, src[0].obs_mask, act.x0);
         } else if (cfg->discrete && g_embed_disc_fast && lay.k_in <= 128) {
             const int KI = lay.k_in;
             const size_t smem = sizeof(float) * ((size_t)KI * (d + 4) + d + ((cfg->vocab * cfg->embed_per_obs + 3) & ~3) + (size_t)ED_TOK * KI);
@@ -747,7 +747,7 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         } else {
             dim3 grid(dtqn_cdiv(Tg * (d / 4), 256), 1, G);
             embed_kernel<<<grid, 256, 0, st>>>(P, S, *cfg, lay.emb_table, lay.emb_w, lay.emb_b, lay.pos, n_seq, L,
-                                                cfg->discrete ? (float)(cfg->vocab - 1) : -5.0f, act.x0);
+                                                src[0].obs_mask, act.x0);
         }
         prof_end(PROF_EMBED, st, 2.0 * (double)T * lay.k_in * d);
         DTQN_LAUNCH_CHECK();

@@ -32,7 +32,7 @@ sqnorm_kernel(const float* __restrict__ g, long long n, float scale, float* __re
 __global__ void __launch_bounds__(OPT_THREADS)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n, float scale, float max_norm, float lr, float beta1, float beta2, float eps,
-                 const long long* __restrict__ step, const float* __restrict__ partial, int n_partial,
+                 long long* __restrict__ step, const float* __restrict__ partial, int n_partial,
                  float* __restrict__ stats, int* __restrict__ flags, float* __restrict__ ring, int ring_len) {
     __shared__ float s_coef;
     __shared__ int s_bad;
@@ -45,8 +45,10 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
         s_coef = fminf(1.0f, max_norm / (total + 1e-6f));       // clip_coef clamped to 1
         if (blockIdx.x == 0) {
             stats[7] = total;
-            if (bad) flags[0] = 1;
-            if (ring) {
+            // error_if_nonfinite (agents/dtqn.py:257-261 raises before optimizer.step): no update, no statistics row, and the
+            // step index is handed back (nobody reads it on this path: every CTA returns before the bias correction)
+            if (bad) { flags[0] = 1; *step -= 1; }
+            else if (ring) {
                 float* row = ring + ((*step - 1) % ring_len) * 8;
                 for (int k = 0; k < 7; ++k) row[k] = stats[k];
                 row[7] = total;
@@ -56,7 +58,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     __syncthreads();
     if (s_bad) return;                                          // error_if_nonfinite: parameters untouched
     const float coef = s_coef * scale;
-    const double t = (double)(*step);
+    const double t = (double)(*reinterpret_cast<const volatile long long*>(step));
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
     const float neg_step = (float)(-(double)lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
@@ -75,7 +77,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 // second half of the update on its own (the P2P gradient exchange in p2p.cu produces `partial` itself)
 int launch_clip_adam_only(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float grad_scale,
-                          float max_norm, float lr, float beta1, float beta2, float eps, const long long* step,
+                          float max_norm, float lr, float beta1, float beta2, float eps, long long* step,
                           const float* partial, int n_partial, float* stats, int* flags, float* ring, int ring_len,
                           cudaStream_t st) {
     int blocks = dtqn_cdiv(n, OPT_THREADS * 4);
@@ -101,7 +103,7 @@ extern "C" int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float
     sqnorm_kernel<<<blocks, OPT_THREADS, 0, st>>>(grads, n, grad_scale, scratch, (long long*)step_counter);
     DTQN_LAUNCH_CHECK();
     clip_adam_kernel<<<blocks, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1,
-                                                    beta2, eps, (const long long*)step_counter, scratch, blocks,
+                                                    beta2, eps, (long long*)step_counter, scratch, blocks,
                                                     stats_out, flags_out, stats_ring, stats_ring ? ring_len : 1);
     prof_end(PROF_ADAM, st, 32.0 * (double)n);     // 28 B/param Adam + 4 B/param norm pass
     DTQN_LAUNCH_CHECK();

@@ -102,7 +102,9 @@ p2p_reduce_sqnorm_kernel(P2PPeers peers, int rank, int world, long long n, float
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < P2P_THREADS / 32; ++w) t += red[w];
-        partial[blockIdx.x] = t;
+        // a bounded wait expired (a peer never arrived): the sum may be incomplete -> poison the norm so clip + Adam skips
+        // the update and raises the non-finite flag instead of applying a partial gradient
+        partial[blockIdx.x] = ld_volatile_u32(&mine->error) ? __int_as_float(0x7fc00000) : t;
     }
     p2p_barrier(peers, rank, world, e, true);
     if (threadIdx.x == 0) {
@@ -119,7 +121,7 @@ p2p_reduce_sqnorm_kernel(P2PPeers peers, int rank, int world, long long n, float
 }  // namespace
 
 int launch_clip_adam_only(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float grad_scale,
-                          float max_norm, float lr, float beta1, float beta2, float eps, const long long* step,
+                          float max_norm, float lr, float beta1, float beta2, float eps, long long* step,
                           const float* partial, int n_partial, float* stats, int* flags, float* ring, int ring_len,
                           cudaStream_t st);
 
@@ -193,7 +195,7 @@ extern "C" int dtqn_allreduce_clip_adam(float* params, void* const* bases, int32
 #undef P2P_LAUNCH
     DTQN_LAUNCH_CHECK();
     int rc = launch_clip_adam_only(params, grads_reduced, exp_avg, exp_avg_sq, n, scale, max_norm, lr, beta1, beta2, eps,
-                                   (const long long*)step_counter, scratch, P2P_BLOCKS, stats_out, flags_out, stats_ring,
+                                   (long long*)step_counter, scratch, P2P_BLOCKS, stats_out, flags_out, stats_ring,
                                    stats_ring ? ring_len : 1, st);
     prof_end(PROF_ADAM, st, (32.0 + 4.0 * world) * (double)n);
     return rc;

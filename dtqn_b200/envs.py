@@ -44,7 +44,9 @@ class BatchedEnv:
     """n_envs lockstep instances of one registered env id, stepped by the sm_100a kernels in csrc/env.cu."""
 
     def __init__(self, env_id: str, n_envs: int, seed: int = 1, device=None, seeds=None,
-                 max_episode_steps: Optional[int] = None):
+                 max_episode_steps: Optional[int] = None, agent_stream_of: Optional["BatchedEnv"] = None):
+        """``agent_stream_of``: share another instance's agent-side streams (the reference has ONE global RNG.rng, drawn by
+        the training loop and by run.evaluate alike -- utils/random.py:31, agents/dtqn.py:78, utils/context.py:50)."""
         if env_id not in ENV_SPECS:
             raise ValueError(f"Environment with id {env_id} not found (hot path covers {sorted(ENV_SPECS)})")
         dev = _lib.require_cuda(device)
@@ -57,7 +59,11 @@ class BatchedEnv:
         words, buf = pcg64_states(self.seeds)
         n = self.n_envs
         self.rng, self.rng_buf = _u64(words, dev), torch.from_numpy(buf.view(np.int32).copy()).to(dev)
-        self.arng, self.arng_buf = self.rng.clone(), self.rng_buf.clone()
+        if agent_stream_of is not None:
+            assert agent_stream_of.n_envs == self.n_envs
+            self.arng, self.arng_buf = agent_stream_of.arng, agent_stream_of.arng_buf
+        else:
+            self.arng, self.arng_buf = self.rng.clone(), self.rng_buf.clone()
         self.pos = torch.zeros(n, dtype=torch.float64, device=dev)
         self.vel = torch.zeros(n, dtype=torch.float64, device=dev)
         self.heaven = torch.ones(n, dtype=torch.int8, device=dev)
@@ -69,6 +75,7 @@ class BatchedEnv:
         self.block_counts = torch.zeros((n + 255) // 256, dtype=torch.int32, device=dev)
         self.ep_stats = torch.zeros(4, dtype=torch.int64, device=dev)
         self.ep_return = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.env_acc = torch.zeros((n, 4), dtype=torch.int32, device=dev)   # per env: episodes, return, length, successes
         # step outputs (reused every step)
         self.actions = torch.zeros(n, dtype=torch.int32, device=dev)
         self.obs_out = torch.zeros((n, O), dtype=torch.float32, device=dev)
@@ -77,13 +84,14 @@ class BatchedEnv:
         self.truncated_out = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.success_out = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.struct = _lib.EnvStruct(
-            kind=kind, n_envs=n, obs_dim=O, num_actions=A, max_episode_steps=self.max_episode_steps, _pad=0,
+            kind=kind, n_envs=n, obs_dim=O, num_actions=A, max_episode_steps=self.max_episode_steps,
+            stat_episodes_per_env=0,
             rng=_lib.ptr(self.rng), rng_buf=_lib.ptr(self.rng_buf), arng=_lib.ptr(self.arng),
             arng_buf=_lib.ptr(self.arng_buf), pos=_lib.ptr(self.pos), vel=_lib.ptr(self.vel),
             heaven=_lib.ptr(self.heaven), cards=_lib.ptr(self.cards), shown=_lib.ptr(self.shown),
             cur=_lib.ptr(self.cur), elapsed=_lib.ptr(self.elapsed), done_flag=_lib.ptr(self.done_flag),
             block_counts=_lib.ptr(self.block_counts), ep_stats=_lib.ptr(self.ep_stats),
-            ep_return=_lib.ptr(self.ep_return))
+            ep_return=_lib.ptr(self.ep_return), env_acc=_lib.ptr(self.env_acc))
         self.replay = None
         self.context = None
 
@@ -96,6 +104,10 @@ class BatchedEnv:
 
     def _cx(self):
         return C.byref(self.context.struct) if self.context is not None else None
+
+    def count_episodes_per_env(self, k: int) -> None:
+        """k > 0: only each env's first k finished episodes (since reset_all) enter ep_stats / env_acc; 0: all of them."""
+        self.struct.stat_episodes_per_env = int(k)
 
     def reset_all(self) -> None:
         _lib.check(_lib.lib.dtqn_env_reset_all(C.byref(self.struct), self._rb(), self._cx(), _lib.stream_ptr()),

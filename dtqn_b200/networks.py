@@ -22,7 +22,7 @@ class NetCfg(C.Structure):
 
 class ObsSrc(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("seq_stride", C.c_int64), ("timestep", C.c_void_p), ("ring_len", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("obs_mask", C.c_float)]
 
 
 _l = _lib.lib
@@ -215,7 +215,7 @@ class DTQN(nn.Module):
         assert O == self.obs_dim, f"Obs dim is incorrect. Expected {self.obs_dim} got {O}"          # dtqn.py:177-179
         x = obss.to(device=self.flat.device, dtype=torch.float32).contiguous()
         q = torch.empty((B, L, self.num_actions), dtype=torch.float32, device=self.flat.device)
-        src = ObsSrc(obs=x.data_ptr(), seq_stride=L * O, timestep=None, ring_len=0, _pad=0)
+        src = ObsSrc(obs=x.data_ptr(), seq_stride=L * O, timestep=None, ring_len=0, obs_mask=0.0)
         forward_groups(self, [self], [src], B, L, q_mode=0, save=0, q_out=q)
         return q
 

@@ -80,7 +80,8 @@ def run_experiment(args):
     tr = BatchedTrainer(args.envs[0], args.n_envs, seed=args.seed, device=device, inner_embed=args.in_embed,
                         heads=args.heads, layers=args.layers, context=args.context, batch=args.batch,
                         buf_size=max(args.buf_size, 8 * args.n_envs * 200), lr=args.lr, tuf=args.tuf,
-                        gamma=args.discount, history=args.history, num_steps=args.num_steps, obs_embed=args.obs_embed)
+                        gamma=args.discount, history=args.history, num_steps=args.num_steps, obs_embed=args.obs_embed,
+                        pos=args.pos, max_episode_steps=args.max_episode_steps)
     rank = tr.rank
     if rank == 0:
         n = sum(p.numel() for p in tr.agent.policy_network.parameters())
@@ -94,7 +95,14 @@ def run_experiment(args):
         f"_identity={args.identity}_history={args.history}_pos={args.pos}_bag={args.bag_size}_seed={args.seed}")
     ckpt = policy_path + (f"_rank{rank}" if world > 1 else "")
     from dtqn_b200.checkpoint import RunningAverage
-    if os.path.exists(ckpt + "_mini_checkpoint.pt"):                                             # run.py:469-490
+    have_ckpt = os.path.exists(ckpt + "_mini_checkpoint.pt")
+    if world > 1:                     # every rank must take the same branch: resume only if ALL ranks hold their files
+        flag = torch.tensor([int(have_ckpt)], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if have_ckpt and not bool(flag.item()):
+            print(f"[rank {rank}] ignoring {ckpt}_mini_checkpoint.pt: another rank has no checkpoint; starting fresh")
+        have_ckpt = bool(flag.item())
+    if have_ckpt:                                                                                 # run.py:469-490
         done_steps = tr.agent.load_mini_checkpoint(ckpt)["step"]
         print(f"Found a mini checkpoint that completed {done_steps} training steps.")
         if done_steps >= args.num_steps:
@@ -124,7 +132,9 @@ def run_experiment(args):
     for timestep in range(tr.agent.num_train_steps, args.num_steps):
         tr.train_iteration()
         if timestep % args.eval_frequency == 0:
-            sr, ret, length = tr.evaluate(max(1, args.eval_episodes // 10))
+            # run.py:315: `eval_episodes` greedy episodes; here every lockstep eval env of every rank plays the same number
+            # of episodes, the smallest count that reaches eval_episodes in total
+            sr, ret, length = tr.evaluate(max(1, -(-args.eval_episodes // (args.n_envs * world))))
             mean_success_rate.add(sr); mean_reward.add(ret); mean_episode_length.add(length)     # run.py:316-318
             if rank == 0:
                 hours = (time.time() - start) / 3600

@@ -19,18 +19,21 @@ class BatchedTrainer:
                  inner_embed: int = 64, heads: int = 8, layers: int = 2, context: int = 50, batch: int = 32,
                  buf_size: Optional[int] = None, lr: float = 3e-4, tuf: int = 10_000, gamma: float = 0.99,
                  history: Optional[int] = None, num_steps: int = 2_000_000, obs_embed: int = 8,
-                 trunc_context_obs: bool = True):
+                 trunc_context_obs: bool = True, pos: str = "learned", max_episode_steps: Optional[int] = None,
+                 a_embed: int = 0, dropout: float = 0.0, identity: bool = False, gate: str = "res"):
         rank, world = rank_world()
         self.rank, self.world = rank, world
         self.device = _lib.require_cuda(device)
-        self.env = BatchedEnv(env_id, n_envs, seed=shard_seed(seed, rank, n_envs), device=self.device)
+        self.env = BatchedEnv(env_id, n_envs, seed=shard_seed(seed, rank, n_envs), device=self.device,
+                              max_episode_steps=max_episode_steps if max_episode_steps and max_episode_steps > 0 else None)
         self.eval_env = None
         E = self.env.max_episode_steps
         if buf_size is None:
             buf_size = max(500_000, 8 * n_envs * E)           # ring >= 8 slots per env so it never wraps onto open episodes
         torch.manual_seed(seed)                              # identical initial parameters on every rank
-        self.agent = get_agent("DTQN", [self.env], obs_embed, 0, inner_embed, buf_size, self.device, lr, batch, context,
-                               E, history or context, tuf, gamma, num_heads=heads, num_layers=layers, n_envs=n_envs,
+        self.agent = get_agent("DTQN", [self.env], obs_embed, a_embed, inner_embed, buf_size, self.device, lr, batch, context,
+                               E, history or context, tuf, gamma, num_heads=heads, num_layers=layers, dropout=dropout,
+                               identity=identity, gate=gate, pos=pos, n_envs=n_envs,
                                trunc_context_obs=trunc_context_obs, sample_seed=seed * 7919 + rank)
         if world > 1:
             broadcast_parameters(self.agent.policy_network.flat, src=0)
@@ -56,7 +59,7 @@ class BatchedTrainer:
         self._graph = None
         # exploration schedule mirrored on the device: a replayed graph reads / anneals it without any host write
         self._eps_state = torch.zeros(3, dtype=torch.float64, device=self.device)
-        self._eps_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._eps_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
 
     def prepopulate(self, lockstep_steps: int) -> None:
         """run.prepopulate (run.py:380-405): uniform-random actions from the agent-side stream."""
@@ -79,8 +82,8 @@ class BatchedTrainer:
                                             getattr(self.eps, "duration", 1)], dtype=torch.float64))
 
     def _device_epsilon(self) -> None:
-        _lib.check(_lib.lib.dtqn_eps_anneal(C.c_void_p(self._eps_state.data_ptr()), C.c_void_p(self._eps_dev.data_ptr()),
-                                            _lib.stream_ptr()), "dtqn_eps_anneal")
+        _lib.check(_lib.lib.dtqn_eps_anneal(self._eps_state.data_ptr(), self._eps_dev.data_ptr(), _lib.stream_ptr()),
+                   "dtqn_eps_anneal")
 
     def enable_graphs(self) -> None:
         """Capture one loop iteration (acting forward, env step + roll, sample, gather, 3 forwards, TD, backward and --
@@ -214,23 +217,36 @@ class BatchedTrainer:
 
     def make_eval_env(self) -> BatchedEnv:
         if self.eval_env is None:
-            self.eval_env = BatchedEnv(self.env.env_id, self.n_envs, seeds=self.env.seeds, device=self.device)
+            # same seeds as the train envs (utils/random.py:26-29) and the SAME agent-side streams: the reference's
+            # evaluation draws from the one global RNG.rng the training loop uses
+            self.eval_env = BatchedEnv(self.env.env_id, self.n_envs, seeds=self.env.seeds, device=self.device,
+                                       max_episode_steps=self.env.max_episode_steps, agent_stream_of=self.env)
             self.eval_env.attach(None, self.agent.eval_context)
         return self.eval_env
 
     @torch.no_grad()
-    def evaluate(self, eval_episodes_per_env: int = 1, max_steps: Optional[int] = None):
+    def evaluate(self, eval_episodes_per_env: int = 1, max_steps: Optional[int] = None, reduce_ranks: bool = True):
         """run.evaluate (run.py:187-243): greedy policy on a separate set of envs seeded like the train envs
-        (utils/random.py:26-29), no replay writes.  Returns (success_rate, mean_return, mean_episode_length)."""
+        (utils/random.py:26-29), no replay writes, EXACTLY ``eval_episodes_per_env`` episodes per env: each env's first k
+        finished episodes are counted (per-env counter in the step kernel), later ones are ignored, so short episodes are
+        not over-represented.  Sums are reduced over ranks.  Returns (success_rate, mean_return, mean_episode_length);
+        ``self.last_eval_per_env`` keeps the per-env [n, 4] sums (episodes, return, length, successes) of this rank."""
         agent = self.agent
         ev = self.make_eval_env()
+        k = int(eval_episodes_per_env)
         agent.eval_on()
+        ev.count_episodes_per_env(k)
         ev.reset_all()
-        target = eval_episodes_per_env * self.n_envs
-        steps = max_steps or (eval_episodes_per_env + 1) * ev.max_episode_steps
-        for _ in range(steps):
+        steps = max_steps or k * ev.max_episode_steps            # every episode ends within max_episode_steps (TimeLimit)
+        for t in range(steps):
             agent.act_and_step(ev, 0.0, record=False)
+            if t % 25 == 24 and bool((ev.env_acc[:, 0] >= k).all().item()):
+                break
         agent.eval_off()
-        ret, length, succ, n = [int(v) for v in ev.ep_stats.tolist()]
+        self.last_eval_per_env = ev.env_acc.clone()
+        tot = ev.env_acc.sum(dim=0, dtype=torch.int64)
+        if reduce_ranks and self.world > 1:
+            dist.all_reduce(tot)
+        n, ret, length, succ = [int(v) for v in tot.tolist()]
         n = max(n, 1)
         return succ / n, ret / n, length / n

@@ -7,9 +7,13 @@
  * Conventions (all entry points):
  *   - plain C: raw DEVICE pointers + explicit sizes inside POD structs, a cudaStream_t passed as void*;
  *   - return int: 0 = ok, < 0 = invalid argument (DTQN_E_*), > 0 = cudaError_t of a failed launch;
- *   - never allocates, never synchronises, never throws; the caller (PyTorch) owns every buffer and keeps it
- *     alive until the stream has passed the call;
- *   - no global mutable state: re-entrant across processes (one process per GPU).
+ *   - compute entry points never allocate, never synchronise, never throw; the caller (PyTorch) owns every buffer and
+ *     keeps it alive until the stream has passed the call.  Exceptions, named where they are declared: dtqn_p2p_alloc /
+ *     _open / _close / _free own the IPC-exported exchange buffer (cudaMalloc + cudaIpc*), dtqn_p2p_error /
+ *     dtqn_tc_error / dtqn_profile_read copy one word back (they synchronise);
+ *   - no per-call global state: one process per GPU, re-entrant across processes.  The dtqn_set_* switches and
+ *     dtqn_profile_enable are process-global tuning / measurement knobs (defaults are the product path); set them before
+ *     launching work, not concurrently with it.
  */
 #ifndef DTQN_B200_H
 #define DTQN_B200_H
@@ -20,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DTQN_ABI_VERSION 3
+#define DTQN_ABI_VERSION 4
 
 #define DTQN_E_ARG      (-1)  /* null pointer / out-of-range size */
 #define DTQN_E_UNSUPPORTED (-2)
@@ -43,7 +47,8 @@ typedef struct dtqn_env {
     int32_t obs_dim;            /* 3 (CarFlag) | 10 (Memory) */
     int32_t num_actions;        /* 3 | 10 */
     int32_t max_episode_steps;  /* TimeLimit: 200 | 50 (envs/__init__.py:31-48) */
-    int32_t _pad;
+    int32_t stat_episodes_per_env; /* > 0: only the first k finished episodes of each env enter ep_stats / env_acc
+                                      (run.evaluate's fixed episode count, run.py:214-233); 0: every episode */
     uint64_t* rng;              /* [4][n] env np_random: state_hi, state_lo, inc_hi, inc_lo */
     uint32_t* rng_buf;          /* [2][n] has_uint32, uinteger */
     uint64_t* arng;             /* [4][n] agent-side stream = the reference's global RNG.rng (utils/random.py:31) */
@@ -59,6 +64,7 @@ typedef struct dtqn_env {
     int32_t*  block_counts;     /* [ceil(n/256)] scratch: episodes finished per CTA in this step */
     int64_t*  ep_stats;         /* [4] running sums over finished episodes: return, length, successes, episodes */
     int32_t*  ep_return;        /* [n] return of the running episode (rewards are integers in both envs) */
+    int32_t*  env_acc;          /* nullable [n][4] per-env sums over its counted episodes: episodes, return, length, successes */
 } dtqn_env;
 
 /* ---- device-resident episode-major replay buffer: dtqn/buffers/replay_buffer.py:19-135 --------------------------
@@ -95,7 +101,8 @@ typedef struct dtqn_context {
 
 typedef struct dtqn_step_io {
     int32_t action_mode;        /* DTQN_ACT_* */
-    float   epsilon;
+    int32_t _pad;
+    double  epsilon;            /* f64 like the reference: RNG.rng.random() < epsilon compares two doubles (agents/dtqn.py:78) */
     int32_t* actions;           /* [n] in (GIVEN) / out (RANDOM, EPS_GREEDY) */
     const float* q_last;        /* [n, A] greedy Q of the last context position (EPS_GREEDY) */
     float*   obs_out;           /* [n, O] observation returned by env.step (terminal obs when done); nullable */
@@ -103,7 +110,7 @@ typedef struct dtqn_step_io {
     uint8_t* done_out;          /* [n] env done incl. TimeLimit; nullable */
     uint8_t* truncated_out;     /* [n] info["TimeLimit.truncated"]; nullable */
     uint8_t* success_out;       /* [n] info["is_success"]; nullable */
-    const float* epsilon_dev;   /* nullable: device scalar read instead of `epsilon` (CUDA-graph replay) */
+    const double* epsilon_dev;  /* nullable: device f64 scalar read instead of `epsilon` (CUDA-graph replay) */
 } dtqn_step_io;
 
 int dtqn_version(void);
@@ -111,7 +118,7 @@ int dtqn_version(void);
 /* Exploration schedule on the device (LinearAnneal.anneal, utils/epsilon_anneal.py:33-34; run.py:298): writes the current
  * value to *eps_out (the `epsilon_dev` of the next dtqn_env_step) and advances state = {val, min, duration} (3 doubles,
  * device memory) by val <- max(min, val - (val - min) / duration) in double precision, bit-identical to the host loop. */
-int dtqn_eps_anneal(double* state, float* eps_out, void* stream);
+int dtqn_eps_anneal(double* state, double* eps_out, void* stream);
 
 /* env.reset() of every instance + agent.context_reset(obs) (run.py:287-288): allocates slots 0..n-1, stores the first
  * observation (ReplayBuffer.store_obs :88-92) and resets the contexts.  rb / cx may be NULL. */
@@ -161,7 +168,7 @@ typedef struct dtqn_obs_src {
     int64_t        seq_stride;   /* floats */
     const int32_t* timestep;     /* nullable */
     int32_t        ring_len;
-    int32_t        _pad;
+    float          obs_mask;     /* value of context rows not yet written (Context.reset fill, utils/context.py:46): -5 | 8 */
 } dtqn_obs_src;
 
 /* Number of floats of the flat parameter buffer, and the offset of every tensor in it, in this fixed order:

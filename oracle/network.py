@@ -151,3 +151,53 @@ def trainable_keys(sd, pos="learned"):
             continue
         ks.append(k)
     return ks
+
+
+class ModuleNet(torch.nn.Module):
+    """The same network built from the torch.nn blocks the reference instantiates (nn.MultiheadAttention batch_first with a
+    float causal mask, nn.LayerNorm, nn.Linear / nn.Embedding; dtqn.py:61-156, transformer.py:20-53), parameter names chosen
+    so a reference-compatible state_dict loads unchanged.  Default flags only (gate res, no identity / action embedding).
+    Used by the CPU baseline loop so the port executes the reference's own library calls op for op (the closed form above
+    is the numerical checker; ``tests/test_oracle_vs_golden.py`` pins the two against each other)."""
+
+    class _Block(torch.nn.Module):
+        def __init__(self, d, heads, ctx):
+            super().__init__()
+            nn = torch.nn
+            self.layernorm1, self.layernorm2 = nn.LayerNorm(d), nn.LayerNorm(d)
+            self.attention = nn.MultiheadAttention(d, heads, dropout=0.0, batch_first=True)
+            self.ffn = nn.Sequential(nn.Linear(d, 4 * d), nn.ReLU(), nn.Linear(4 * d, d), nn.Dropout(0.0))
+            self.attn_mask = nn.Parameter(torch.zeros(ctx, ctx), requires_grad=False)
+
+        def forward(self, x):
+            L = x.size(1)
+            a, _ = self.attention(x, x, x, attn_mask=self.attn_mask[:L, :L], average_attn_weights=True)
+            x = self.layernorm1(x + torch.relu(a))
+            return self.layernorm2(x + torch.relu(self.ffn(x)))
+
+    class _Holder(torch.nn.Module):
+        pass
+
+    def __init__(self, sd, num_heads):
+        super().__init__()
+        nn = torch.nn
+        ctx, d = sd["position_embedding.position_encoding"].shape[1:]
+        self.obs_embedding = ModuleNet._Holder()
+        if "obs_embedding.observation_embedding.0.weight" in sd:
+            V, E = sd["obs_embedding.observation_embedding.0.weight"].shape
+            K = sd["obs_embedding.observation_embedding.2.weight"].shape[1]
+            self.obs_embedding.observation_embedding = nn.Sequential(nn.Embedding(V, E), nn.Flatten(start_dim=-2), nn.Linear(K, d))
+        else:
+            self.obs_embedding.observation_embedding = nn.Linear(sd["obs_embedding.observation_embedding.weight"].shape[1], d)
+        self.position_embedding = ModuleNet._Holder()
+        self.position_embedding.position_encoding = nn.Parameter(torch.zeros(1, ctx, d))
+        self.transformer_layers = nn.Sequential(*[ModuleNet._Block(d, num_heads, ctx) for _ in range(num_layers_of(sd))])
+        A = sd["ffn.2.weight"].shape[0]
+        self.ffn = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, A))
+        self.load_state_dict(sd)
+
+    def forward(self, obss):
+        B, L = obss.shape[:2]
+        tok = self.obs_embedding.observation_embedding(obss.reshape(B * L, *obss.shape[2:])).reshape(B, L, -1)
+        x = tok + self.position_embedding.position_encoding[:, :L, :]
+        return self.ffn(self.transformer_layers(x))[:, -L:, :]

@@ -266,9 +266,61 @@ def gen_ablations():
     print("wrote forward_ablations.npz")
 
 
+def gen_checkpoint():
+    """A checkpoint WRITTEN BY THE REFERENCE (DqnAgent.save_checkpoint, dqn.py:222-279: `_checkpoint.pt` with pickled
+    utils.logging_utils.RunningAverage objects + the five joblib `.sav` buffers + `_mini_checkpoint.pt`) after a short run,
+    followed by one more reference train() on a recorded batch -> the parameters a correctly resumed agent must reach."""
+    sys.argv = ["run.py"]
+    import run as ref_run
+    import random
+    from utils import epsilon_anneal
+    from utils.logging_utils import RunningAverage
+    out_dir = os.path.join(HERE, "refckpt")
+    os.makedirs(out_dir, exist_ok=True)
+    batch, ctx = 4, 50
+    agent, env = make_agent("DiscreteCarFlag-v0", 64, 2, ctx, batch, buf=4000)
+    ref_run.prepopulate(agent, 1500, [env])
+    agent.eval_off()
+    agent.context_reset(env.reset())
+    eps = epsilon_anneal.LinearAnneal(1.0, 0.1, 300)
+    random.seed(5)
+    for _ in range(40):                                     # the loop body of run.train (run.py:290-298)
+        if ref_run.step(agent, env, eps):
+            agent.replay_buffer.flush()
+            agent.context_reset(env.reset())
+        agent.train()
+        eps.anneal()
+    succ, rew, length = RunningAverage(10), RunningAverage(10), RunningAverage(10)
+    for v in (0.0, 0.5, 1.0):
+        succ.add(v); rew.add(-v); length.add(100 * v + 7)
+    agent.save_checkpoint(os.path.join(out_dir, "ref"), None, succ, rew, length, eps)
+    rb = agent.replay_buffer
+    out = {"meta": np.array([64, 2, ctx, batch, 8, agent.num_train_steps]), "epsilon": np.array([eps.val]),
+           "replay_pos": np.array(rb.pos), "td_errors_mean": np.array([agent.td_errors.mean()]),
+           "succ_mean": np.array([succ.mean()])}
+    state = random.getstate()
+    batch_np = rb.sample(batch)
+    random.setstate(state)
+    valid = [i for i in range(min(rb.pos[0], rb.max_size)) if i != rb.pos[0] % rb.max_size]
+    eps_idx = np.array([random.choice(valid) for _ in range(batch)])
+    starts = np.array([random.randint(0, max(0, int(rb.episode_lengths[e]) - rb.context_len)) for e in eps_idx])
+    out["episodes"], out["starts"] = eps_idx, starts
+    for name, arr in zip(("obss", "actions", "rewards", "next_obss", "next_actions", "dones", "eplens"), batch_np):
+        out["batch/" + name] = np.asarray(arr).copy()
+    rb.sample = lambda bs, b=batch_np: b
+    agent.train()
+    out.update(sd_np(agent.policy_network.state_dict(), "after/"))
+    out["after_grad_norm"] = np.array([list(agent.grad_norms.q)[-1]])
+    np.savez_compressed(os.path.join(out_dir, "expect.npz"), **out)
+    print("wrote refckpt/", sorted(os.listdir(out_dir)))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ablations":
         gen_ablations()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        gen_checkpoint()
         sys.exit(0)
     np.savez_compressed(os.path.join(HERE, "env_carflag.npz"), **gen_env("DiscreteCarFlag-v0", 24, 700))
     np.savez_compressed(os.path.join(HERE, "env_memory.npz"), **gen_env("Memory-5-v0", 24, 400))
@@ -279,3 +331,4 @@ if __name__ == "__main__":
     gen_train("Memory-5-v0", 128, 1, 50, 8, 1500, 2, "memory")
     gen_acting("DiscreteCarFlag-v0", 64, 50, 260, "carflag")
     gen_ablations()
+    gen_checkpoint()

@@ -70,3 +70,33 @@ def test_running_average_window():
         ra.add(v)
     assert ra.mean() == 3.0 and ra.state() == {"size": 3, "values": [2.0, 3.0, 4.0]}
     assert ck.RunningAverage.from_state(ra.state()).mean() == 3.0
+
+
+def test_reference_written_checkpoint_unpickles_without_the_reference_package():
+    """tests/golden/refckpt/ref_checkpoint.pt was written by the reference's DqnAgent.save_checkpoint (dqn.py:222-279) and
+    pickles ``utils.logging_utils.RunningAverage`` objects; the loader must read it where that package does not exist."""
+    import os
+    import sys
+    import pickle
+    import numpy as np
+    import pytest
+    assert "utils.logging_utils" not in sys.modules
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refckpt")
+    c = ck.read_checkpoint_file(os.path.join(d, "ref_checkpoint.pt"))
+    z = np.load(os.path.join(d, "expect.npz"))
+    assert c["step"] == int(z["meta"][5]) and c["replay_buffer_pos"] == [int(z["replay_pos"][0]), 0]
+    assert abs(c["epsilon"] - float(z["epsilon"][0])) == 0.0
+    assert abs(ck.RunningAverage.from_state(c["td_errors"]).mean() - float(z["td_errors_mean"][0])) < 1e-9
+    assert abs(ck.RunningAverage.from_state(c["episode_successes"]).mean() - float(z["succ_mean"][0])) < 1e-12
+    assert set(c["optimizer_state_dict"]) == {"state", "param_groups"}
+    assert ck.load_mini_checkpoint(os.path.join(d, "ref"))["step"] == c["step"]
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    import io
+    buf = io.BytesIO()
+    torch.save({"x": Evil()}, buf)
+    buf.seek(0)
+    with pytest.raises(pickle.UnpicklingError):
+        torch.load(buf, weights_only=False, pickle_module=ck._CheckpointPickle)

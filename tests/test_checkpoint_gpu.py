@@ -116,3 +116,32 @@ def test_reference_style_checkpoint_loads_into_single_env_agent(tmp_path):
     x = torch.randn(2, 50, 3, device="cuda")
     assert torch.equal(a.agent.policy_network(x), b.agent.policy_network(x))
     assert abs(a.agent.td_errors.mean() - b.agent.td_errors.mean()) < 1e-7
+
+
+def test_reference_written_checkpoint_resumes_like_the_reference(golden_dir):
+    """a `_checkpoint.pt` + five `.sav` buffers WRITTEN BY THE REFERENCE (tests/golden/refckpt, made by
+    gen_golden.py through DqnAgent.save_checkpoint, dqn.py:222-279) load into the CUDA agent: networks, Adam moments + step,
+    replay arrays, statistics windows -- and the next train() on the reference's recorded batch lands on the parameters the
+    reference itself reached after resuming (dqn.py:281-327 -> agents/dtqn.py:162-269)."""
+    from dtqn_b200.agents import DtqnAgent
+    from dtqn_b200.networks import DTQN
+    d = os.path.join(golden_dir, "refckpt")
+    z = np.load(os.path.join(d, "expect.npz"))
+    dm, layers, ctx, B, heads, steps = [int(v) for v in z["meta"]]
+    mk = lambda: DTQN(3, 3, 8, 0, dm, heads, layers, ctx, pos="learned", device="cuda")
+    agent = DtqnAgent(mk, 4000, "cuda", 3, 200, -5, 3, False, batch_size=B, context_len=ctx)
+    wandb_id, succ, rew, length, eps = agent.load_checkpoint(os.path.join(d, "ref"))
+    assert wandb_id is None and agent.num_train_steps == steps and int(agent.opt_step.item()) == steps
+    assert eps == float(z["epsilon"][0]) and abs(succ.mean() - float(z["succ_mean"][0])) < 1e-12
+    assert abs(agent.td_errors.mean() - float(z["td_errors_mean"][0])) < 1e-6
+    rb = agent.replay_buffer
+    assert rb.pos == [int(z["replay_pos"][0]), 0] and rb.can_sample(B)
+    out = rb.sample(B, indices=(torch.from_numpy(z["episodes"]).int().cuda(), torch.from_numpy(z["starts"]).int().cuda()))
+    for got, name in zip(out, ("obss", "actions", "rewards", "next_obss", "next_actions", "dones", "eplens")):
+        assert np.array_equal(got.cpu().numpy(), z["batch/" + name]), name
+    agent.train(indices=(torch.from_numpy(z["episodes"]).int().cuda(), torch.from_numpy(z["starts"]).int().cuda()))
+    agent.check_finite()
+    assert abs(float(agent.stats[7]) - float(z["after_grad_norm"][0])) <= 1e-4 * max(1.0, float(z["after_grad_norm"][0]))
+    for k, p in agent.policy_network.state_dict().items():
+        if not k.endswith("attn_mask"):
+            assert np.abs(p.cpu().numpy() - z["after/" + k]).max() < 2e-5, k

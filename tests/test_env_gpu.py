@@ -147,3 +147,65 @@ def test_replay_ring_multi_env_invariants():
         assert n[i] == min(ctx, t + 1)
         want = np.trunc(obss[slots[i], t + 1 - n[i]: t + 1])
         assert np.array_equal(win[i, : n[i]], want), i
+
+
+@pytest.mark.parametrize("eps_on_device", [False, True])
+def test_eps_greedy_stream_matches_reference(golden_dir, eps_on_device):
+    """the N = 1 device loop at epsilon = 0.3 reproduces the reference's recorded acting loop draw for draw
+    (agents/dtqn.py:76-107 through run.step, run.py:356-377): RNG.rng.random() < eps as an f64 comparison, integers(A)
+    when exploring, argmax of the network's last-position Q otherwise; the Context window the network sees, the action,
+    the observation / reward / done the env returns and the buffer_done the replay stores are compared every step."""
+    from dtqn_b200.agents import DtqnAgent
+    from dtqn_b200.envs import BatchedEnv
+    from dtqn_b200.networks import DTQN
+    z = np.load(os.path.join(golden_dir, "acting_carflag.npz"))
+    d, layers, ctx, heads = [int(v) for v in z["meta"]]
+
+    def mk():
+        net = DTQN(3, 3, 8, 0, d, heads, layers, ctx, pos="learned", device="cuda")
+        net.load_state_dict({k[len("policy/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("policy/")})
+        return net
+    agent = DtqnAgent(mk, 50_000, "cuda", 3, 200, -5, 3, False, context_len=ctx, n_envs=1)
+    env = BatchedEnv("DiscreteCarFlag-v0", 1, seed=1, device="cuda")
+    env.reset_all(); env.reset_all()                 # get_agent's two hidden env.reset() (env_processing.py:67)
+    rb = agent.replay_buffer
+    env.attach(rb, agent.train_context)
+    env.reset_all()                                  # agent.context_reset(env.reset())
+    eps_dev = torch.tensor([0.3], dtype=torch.float64, device="cuda") if eps_on_device else None
+    T = len(z["action"])
+    n_explore = 0
+    for t in range(T):
+        win, n = agent.context.windows()
+        n = int(n[0].item())
+        assert n == int(z["ctx_len"][t]), t
+        assert np.array_equal(win[0, :n].cpu().numpy(), z["ctx_obs"][t][:n].astype(np.float32)), t
+        slot, t_ep = int(rb.env_slot[0].item()), int(env.elapsed[0].item())
+        agent.act_and_step(env, 0.0 if eps_on_device else 0.3, epsilon_dev=eps_dev)
+        a = int(env.actions[0].item())
+        assert a == int(z["action"][t]), (t, a, int(z["action"][t]), z["greedy_q"][t])
+        n_explore += a != int(np.argmax(z["greedy_q"][t]))
+        assert np.array_equal(env.obs_out[0].cpu().numpy(), z["obs"][t].astype(np.float32)), t
+        assert float(env.reward_out[0].item()) == float(z["reward"][t]), t
+        assert bool(env.done_out[0].item()) == bool(z["done"][t]), t
+        assert bool(rb.dones[slot, t_ep, 0].item()) == bool(z["buffer_done"][t]), t
+        assert int(rb.actions[slot, t_ep, 0].item()) == a and float(rb.rewards[slot, t_ep, 0].item()) == float(z["reward"][t])
+    assert n_explore > 20 and z["done"].sum() >= 1        # the tape really exercises both branches and an episode roll
+
+
+def test_eps_anneal_on_a_side_stream_tracks_the_host_schedule():
+    """dtqn_eps_anneal takes a 64-bit stream handle (ctypes argtypes declared): run it on a non-default stream and compare
+    the device schedule with LinearAnneal (utils/epsilon_anneal.py:33-34) bit for bit in f64."""
+    from dtqn_b200 import _lib
+    from dtqn_b200.utils import LinearAnneal
+    eps = LinearAnneal(1.0, 0.1, 37)
+    state = torch.tensor([eps.val, eps.min, eps.duration], dtype=torch.float64, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(60):
+            _lib.check(_lib.lib.dtqn_eps_anneal(state.data_ptr(), out.data_ptr(), _lib.stream_ptr()), "dtqn_eps_anneal")
+            side.synchronize()
+            assert float(out.item()) == eps.val
+            eps.anneal()
+    assert float(state[0].item()) == eps.val

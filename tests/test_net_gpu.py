@@ -60,7 +60,7 @@ def _agent_from_golden(z, env, batch):
     d, layers, ctx, B, heads, n_steps = [int(v) for v in z["meta"]]
     mk = lambda: _make_net(z, "policy0/", env)
     O, A, mask, E, disc = (3, 3, -5, 200, False) if env == "carflag" else (10, 10, 8, 50, True)
-    agent = DtqnAgent(mk, 50_000, "cuda", O, E, mask, A, disc, batch_size=B, context_len=ctx, history=ctx)
+    agent = DtqnAgent(mk, 50_000, "cuda", O, E, mask, A, disc, batch_size=batch, context_len=ctx, history=ctx)
     agent.target_network.load_state_dict(_sd(z, "target0/"))
     return agent
 

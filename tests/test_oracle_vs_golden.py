@@ -188,3 +188,38 @@ def test_oracle_ablation_variants_match_reference(golden_dir, name):
                 assert np.abs(g - gr).max() <= 1e-4 * max(np.abs(gr).max(), 1e-6), (name, key)
                 n_checked += 1
             assert n_checked >= 30
+
+
+@pytest.mark.parametrize("fname", ["forward_carflag.npz", "forward_memory.npz"])
+def test_module_form_matches_reference(golden_dir, fname):
+    """oracle.network.ModuleNet (the torch.nn blocks the reference instantiates; the engine of the timed CPU baseline loop)
+    loads the reference's state_dict unchanged and reproduces its recorded Q values."""
+    z = load(golden_dir, fname)
+    net = onet.ModuleNet(sd_from(z, "policy/"), 8)
+    for L in (1, 7, int(z["meta"][2])):
+        with torch.no_grad():
+            q = net(torch.from_numpy(z[f"L{L}/obss"])).numpy()
+        assert np.abs(q - z[f"L{L}/q"]).max() <= 2e-6 * max(1.0, np.abs(z[f"L{L}/q"]).max())
+
+
+def test_baseline_loop_train_step_matches_reference(golden_dir):
+    """The CPU baseline loop's train() (module engine: torch Adam / clip_grad_norm_ / mse_loss) on the reference's recorded
+    batches reproduces its logged statistics and post-Adam parameters."""
+    from oracle.loop import ReferenceLoop
+    z = load(golden_dir, "train_carflag.npz")
+    d, layers, ctx, B, heads, n_steps = [int(v) for v in z["meta"]]
+    lp = ReferenceLoop("DiscreteCarFlag-v0", seed=1, inner_embed=d, heads=heads, layers=layers, context=ctx, batch=B)
+    lp.policy_net.load_state_dict(sd_from(z, "policy0/")); lp.target_net.load_state_dict(sd_from(z, "target0/"))
+    for s in range(n_steps):
+        batch = (torch.from_numpy(z[f"step{s}/obss"]).float(), torch.from_numpy(z[f"step{s}/actions"].astype(np.int64)),
+                 torch.from_numpy(z[f"step{s}/rewards"]), torch.from_numpy(z[f"step{s}/next_obss"]).float(),
+                 torch.from_numpy(z[f"step{s}/next_actions"].astype(np.int64)), torch.from_numpy(z[f"step{s}/dones"]))
+        st = lp._train_module(batch)
+        lp.grad_steps += 1
+        assert abs(st["loss"] - z["stats/td_errors"][s]) <= 1e-5 * max(1.0, abs(z["stats/td_errors"][s]))
+        assert abs(st["grad_norm"] - z["stats/grad_norms"][s]) <= 1e-4 * max(1.0, abs(z["stats/grad_norms"][s]))
+    for k, p in lp.policy_net.state_dict().items():
+        if k.endswith("attn_mask"):                      # -inf entries
+            assert np.array_equal(p.numpy(), z[f"policy{n_steps}/" + k])
+        else:
+            assert np.abs(p.numpy() - z[f"policy{n_steps}/" + k]).max() < 1e-5, k

@@ -122,3 +122,51 @@ def test_two_processes_over_nvlink():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "P2P_WORKER_OK" in out.stdout
+
+
+def test_two_rank_cuda_step_matches_reference_step(golden_dir):
+    """SURVEY section 4(v) on the CUDA path: the reference's batch of 32 windows split 16/16 over two "ranks" (two agents,
+    two exchange buffers, the fused exchange launched concurrently on two streams of one device) -- CUDA forward/backward per
+    rank -> dtqn_allreduce_clip_adam -> the reduced mean gradient equals the reference's step-0 gradient on the whole batch
+    (dtqn/agents/dtqn.py:243-256), the global norm its logged grad norm (:257-263), and after the fixture's three steps
+    both replicas hold the reference's post-Adam parameters (:265)."""
+    import numpy as np
+    from test_net_gpu import _agent_from_golden, _windows
+    from dtqn_b200.parallel import PeerExchange
+    z = np.load(os.path.join(golden_dir, "train_carflag.npz"))
+    d, layers, ctx, B, heads, n_steps = [int(v) for v in z["meta"]]
+    agents = [_agent_from_golden(z, "carflag", B // 2) for _ in range(2)]
+    n = agents[0].policy_network.n_flat
+    ex = [PeerExchange(n, "cuda", r, 2) for r in range(2)]
+    bases = (C.c_void_p * 2)(ex[0].base, ex[1].base)
+    for r in range(2):
+        ex[r].bases = bases
+        agents[r].use_peer_exchange(ex[r])
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for s in range(n_steps):
+        win = _windows(z, s)
+        for r in range(2):
+            half = [w[r * (B // 2):(r + 1) * (B // 2)].contiguous() for w in win]
+            agents[r].forward_backward(*half)
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                agents[r].reduce_and_step()
+        torch.cuda.synchronize()
+        for r in range(2):
+            agents[r].finish_step()
+            agents[r].check_finite()
+        assert torch.equal(ex[0].reduced, ex[1].reduced)
+        assert abs(float(agents[0].stats[7]) - z["stats/grad_norms"][s]) <= 1e-4 * max(1.0, z["stats/grad_norms"][s])
+        if s == 0:
+            grads = agents[0].policy_network.unflatten(ex[0].reduced * 0.5)
+            gmax = max(np.abs(z["step0/grad/" + k]).max() for k in grads if ("step0/grad/" + k) in z.files)
+            for k, g in grads.items():
+                ref_g = z["step0/grad/" + k]
+                err = np.abs(g.cpu().numpy() - ref_g).max()
+                assert err <= 1e-3 * max(np.abs(ref_g).max(), 1e-3 * gmax), (k, err)
+    assert torch.equal(agents[0].policy_network.flat, agents[1].policy_network.flat)          # replicas bit-identical
+    assert torch.equal(agents[0].exp_avg, agents[1].exp_avg) and torch.equal(agents[0].exp_avg_sq, agents[1].exp_avg_sq)
+    for k, p in agents[0].policy_network.state_dict().items():
+        if not k.endswith("attn_mask"):
+            assert np.abs(p.cpu().numpy() - z[f"policy{n_steps}/" + k]).max() < 2e-5, k

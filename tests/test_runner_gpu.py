@@ -123,3 +123,48 @@ def test_host_loop_graphs_match_eager_api():
     assert np.array_equal(a.env.rng_state(), b.env.rng_state())
     assert a.agent.num_train_steps == b.agent.num_train_steps
     assert (a.agent.policy_network.flat - b.agent.policy_network.flat).abs().max().item() < 5e-5
+
+
+def test_evaluate_matches_oracle_greedy_rollouts(golden_dir):
+    """run.evaluate (run.py:187-243) on the device: greedy policy, exactly k episodes per eval env, same seeds as the train
+    envs.  Every env's (return, length, successes) over its k episodes must equal a CPU-oracle greedy rollout of the same
+    seed with the same weights (oracle env + Context + closed-form network), and a second evaluate() continues the eval
+    envs' streams like the reference's persistent eval env does."""
+    import os
+    from oracle import envs as oenvs, network as onet
+    from oracle.pcg64 import PCG64
+    from oracle.replay import ContextOracle
+    z = np.load(os.path.join(golden_dir, "acting_carflag.npz"))
+    sd = {k[len("policy/"):]: torch.from_numpy(z[k]).float() for k in z.files if k.startswith("policy/")}
+    N, K = 24, 2
+    t = _trainer(n_envs=N, seed=11, batch=8)
+    t.agent.policy_network.load_state_dict(sd)
+    first = t.evaluate(K)
+    acc1 = t.last_eval_per_env.cpu().numpy()
+    second = t.evaluate(K)
+    acc2 = t.last_eval_per_env.cpu().numpy()
+    assert (acc1[:, 0] == K).all() and (acc2[:, 0] == K).all()
+    for got, acc in ((first, acc1), (second, acc2)):
+        tot = acc.sum(0)
+        assert got == (tot[3] / tot[0], tot[1] / tot[0], tot[2] / tot[0])
+    mism = 0
+    for i in range(N):
+        env = oenvs.make("DiscreteCarFlag-v0", int(t.env.seeds[i]))
+        cx = ContextOracle(50, -5, 3, 3, PCG64.from_seed(0))
+        for acc in (acc1, acc2):
+            ret = length = succ = 0
+            for _ in range(K):
+                cx.reset(env.reset())
+                done, ep_r = False, 0.0
+                while not done:
+                    obs, _ = cx.window()
+                    with torch.no_grad():
+                        q = onet.forward(sd, torch.as_tensor(obs, dtype=torch.float32).unsqueeze(0), 8)
+                    a = int(torch.argmax(q[0, -1]).item())
+                    o, r, done, info = env.step(a)
+                    cx.add_transition(o, a)
+                    ep_r += r
+                ret += ep_r; length += cx.timestep
+                succ += int(info.get("is_success", False) or ep_r > 0)
+            mism += (int(acc[i, 1]), int(acc[i, 2]), int(acc[i, 3])) != (int(ret), int(length), int(succ))
+    assert mism == 0, f"{mism} of {2 * N} per-env evaluation records differ from the oracle rollout"

@@ -40,7 +40,8 @@ def evaluate(episodes=20):
             obs, _ = eval_ctx.window()
             x = torch.as_tensor(obs, dtype=torch.long if loop.discrete else torch.float32).unsqueeze(0)
             with torch.no_grad():
-                a = int(torch.argmax(onet.forward(loop.trainer.policy, x, loop.heads)[:, -1, :]).item())
+                q = loop.policy_net(x) if loop.engine == "module" else onet.forward(loop.trainer.policy, x, loop.heads)
+                a = int(torch.argmax(q[:, -1, :]).item())
             o, r, done, info = eval_env.step(a)
             eval_ctx.add_transition(o, a)
             ep_r += r
