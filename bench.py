@@ -57,8 +57,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="lockstep envs per GPU")
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--workload", default="carflag", choices=["carflag", "memory"],
-                    help="carflag: BASELINE.json configs[1] (the headline); memory: configs[2] (Memory-5-v0, in-embed 128)")
+    ap.add_argument("--workload", default="carflag", choices=["carflag", "memory", "mixed128"],
+                    help="carflag: BASELINE.json configs[1] (the headline, with a short configs[2] sub-record); memory: configs[2] "
+                         "(Memory-5-v0, in-embed 128); mixed128: configs[4] (CarFlag + Memory-5 groups, ctx=128)")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the Memory-5 sub-record of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
@@ -217,10 +219,129 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def timed_iterations(trainers, steps, warmup, barrier, streams=None):
+    """ms per lockstep iteration of one or more independent trainers (each on its own stream when given), CUDA events."""
+    import torch
+    cur = torch.cuda.current_stream()
+
+    def one():
+        if streams is None:
+            for t in trainers:
+                t.train_iteration()
+            return
+        for t, s in zip(trainers, streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                t.train_iteration()
+        for s in streams:
+            cur.wait_stream(s)
+    for _ in range(warmup):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def memory5_sub_record(dev, n_envs, batch, steps, barrier):
+    """BASELINE.json configs[2] (Memory-5-v0, 4096 batched envs, ctx 50, in-embed 128) as a short sub-record of the default
+    line: the same loop (policy in the loop, 1 grad step per lockstep env step) for `steps` graph-replayed iterations."""
+    import torch
+    from dtqn_b200.runner import BatchedTrainer
+    tr = BatchedTrainer("Memory-5-v0", n_envs, seed=1, device=dev, inner_embed=128, heads=HEADS, layers=LAYERS, context=CTX,
+                        batch=batch)
+    tr.prepopulate(70)
+    while not tr.agent.replay_buffer.can_sample(batch):
+        tr.prepopulate(16)
+    tr.enable_graphs()
+    ms = timed_iterations([tr], steps, 3, barrier)
+    tr.agent.check_finite()
+    rec = {"workload": f"Memory-5-v0, {n_envs} batched envs per GPU, ctx={CTX}, in-embed=128, train batch {batch}", "steps": steps,
+           "ms_per_step": ms, "env_steps_per_sec": n_envs * 1e3 / ms, "grad_steps_per_sec": 1e3 / ms,
+           "acting_forward_algorithmic_TFLOPs_per_sec": 893_440 * n_envs * CTX / (ms * 1e-3) / 1e12}
+    del tr
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_mixed(args):
+    """BASELINE.json configs[4]: CarFlag + Memory-5 at ctx = 128.  The reference cannot run this mix (one
+    agent's buffer / network take envs[0]'s observation width 3 vs 10 and action count 3 vs 10, utils/agent_utils.py:87-107),
+    so the supported reading is two independent agent groups per GPU -- each with its own envs, replay shard, network and
+    optimiser -- stepping in the same iteration on two CUDA streams; value = env-steps/s of both groups and all ranks."""
+    import torch
+    import torch.distributed as dist
+    from dtqn_b200.runner import BatchedTrainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    n_each, ctx = args.envs // 2, 128
+    car = BatchedTrainer("DiscreteCarFlag-v0", n_each, seed=1, device=dev, inner_embed=64, heads=HEADS, layers=LAYERS,
+                         context=ctx, batch=args.batch)
+    mem = BatchedTrainer("Memory-5-v0", n_each, seed=1, device=dev, inner_embed=128, heads=HEADS, layers=LAYERS,
+                         context=ctx, batch=args.batch, max_episode_steps=ctx)
+    for t, n in ((car, 260), (mem, 160)):
+        t.prepopulate(n)
+        while not t.agent.replay_buffer.can_sample(args.batch):
+            t.prepopulate(32)
+        if not args.no_graph:
+            t.enable_graphs()
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    W = max(3, args.warmup)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); time.sleep(0.25)
+    ms = torch.tensor([timed_iterations([car, mem], args.steps, W, barrier, streams)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(ms.item())
+    ms_serial = timed_iterations([car, mem], max(5, args.steps // 4), 1, barrier)
+    ms_car = timed_iterations([car], max(5, args.steps // 4), 1, barrier)
+    ms_mem = timed_iterations([mem], max(5, args.steps // 4), 1, barrier)
+    for t in (car, mem):
+        t.agent.check_finite()
+    if rank == 0:
+        line = {
+            "metric": "env_steps_per_sec", "value": 2 * n_each * world * 1e3 / ms, "unit": "env-steps/s",
+            "grad_steps_per_sec": 2e3 / ms, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mixed DiscreteCarFlag-v0 (in-embed 64) + Memory-5-v0 (in-embed 128, TimeLimit {ctx}), ctx={ctx}, "
+                                   f"{n_each} batched envs per group per GPU, train batch {args.batch} per group, two independent agent "
+                                   "groups per GPU on two CUDA streams (the reference cannot mix these spaces in one agent, SURVEY A-Q9)",
+                       "envs_per_gpu": 2 * n_each, "parallelism": f"dp{world}", "cuda_graphs": not args.no_graph,
+                       "l2": "per-step working set (acting-forward activations of 2 x %d x 128 tokens) exceeds the 126 MB L2; no flush" % n_each},
+            "breakdown": {"both_groups_two_streams_ms": ms, "both_groups_one_stream_ms": ms_serial, "carflag_group_ms": ms_car,
+                          "memory_group_ms": ms_mem},
+            "e2e": None, "roofline": None, "cpu_baseline": None, "clocks": clocks, "gpu_launches": None,
+            "note": "secondary workload line: parity for ctx = 128 is covered by tests (train kernels at ctx 128, acting path per GEMM); "
+                    "the headline line with e2e / roofline / cpu_baseline is the default workload",
+        }
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "mixed128":
+        return run_mixed(args)
 
     import numpy as np
     import torch
@@ -486,6 +607,10 @@ def main():
                             "graph) + sqnorm + clip/Adam kernels"}
         del tr2
 
+    sub = None
+    if world == 1 and args.workload == "carflag" and not args.no_sub_records:
+        sub = {"memory5": memory5_sub_record(dev, N, args.batch, max(20, min(60, args.steps)), barrier)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = time_reference(args.batch)
@@ -511,6 +636,7 @@ def main():
                                             "host obs/reward/done -> agent.train -> host loss")},
             "gpu_launches": launches,
             "replicas_identical": replicas_ok, "exchange_check": exchange_check, "nccl_arm": nccl_arm,
+            "sub_records": sub,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "breakdown": breakdown,
             "acting_forward_algorithmic_TFLOPs_per_sec": FWD_FLOP_PER_TOKEN * N * CTX * world * args.steps / (ms / 1e3) / 1e12,
         }

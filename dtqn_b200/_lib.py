@@ -35,7 +35,7 @@ class ReplayStruct(C.Structure):
 
 class ContextStruct(C.Structure):
     _fields_ = [("context_len", C.c_int32), ("obs_dim", C.c_int32), ("trunc_obs", C.c_int32), ("obs_mask", C.c_float),
-                ("obs", _p), ("timestep", _p)]
+                ("obs", _p), ("timestep", _p), ("action", _p)]
 
 
 class StepIO(C.Structure):

@@ -176,7 +176,8 @@ class DtqnAgent:
         """Q of the last context position of every env ([n_envs, A]) from the device context ring."""
         cx, net = self.context, self.policy_network
         src = ObsSrc(obs=cx.obs.data_ptr(), seq_stride=cx.max_length * cx.env_obs_length,
-                     timestep=cx.timestep_t.data_ptr(), ring_len=cx.max_length, obs_mask=cx.obs_mask)
+                     timestep=cx.timestep_t.data_ptr(), ring_len=cx.max_length, obs_mask=cx.obs_mask,
+                     actions=cx.action.data_ptr(), act_stride=cx.max_length, train_mode=int(net.training))
         forward_groups(net, [net], [src], self.n_envs, self.context_len, q_mode=1, save=0, q_out=self._q_last)
         return self._q_last
 
@@ -197,9 +198,13 @@ class DtqnAgent:
         net, tgt = self.policy_network, self.target_network
         B, L, O = obs_win.shape[0], self.context_len, self.env_obs_length
         stride = (L + 1) * O
-        s_obs = ObsSrc(obs=obs_win.data_ptr(), seq_stride=stride, timestep=None, ring_len=0, obs_mask=float(self.obs_mask))
-        s_next = ObsSrc(obs=obs_win.data_ptr() + 4 * O, seq_stride=stride, timestep=None, ring_len=0, obs_mask=float(self.obs_mask))
-        ws = forward_groups(net, [net, net, tgt], [s_obs, s_next, s_next], B, L, q_mode=0, save=1,
+        # policy(obss, actions) and policy(next_obss, next_actions) in train mode, target(next_obss, next_actions) in eval
+        # mode (agents/dtqn.py:215-233); actions / next_actions are columns [0, L) / [1, L+1) of the (L+1)-column window
+        mk = lambda shift, train: ObsSrc(obs=obs_win.data_ptr() + 4 * O * shift, seq_stride=stride, timestep=None, ring_len=0,
+                                         obs_mask=float(self.obs_mask), actions=act_win.data_ptr() + shift, act_stride=L + 1,
+                                         train_mode=train)
+        s_obs, s_next, s_tgt = mk(0, 1), mk(1, 1), mk(1, 0)
+        ws = forward_groups(net, [net, net, tgt], [s_obs, s_next, s_tgt], B, L, q_mode=0, save=1,
                             q_out=self._q_all)
         st = _lib.stream_ptr()
         _lib.check(_l.dtqn_td_backward(C.byref(net.cfg), net.flat.data_ptr(), C.byref(s_obs), self._q_all.data_ptr(),
@@ -257,7 +262,7 @@ class DtqnAgent:
         cx.timestep_t.zero_()
         self._host_t = 0
         if RNG.rng is not None:                                                  # Context.reset random action padding
-            RNG.rng.integers(self.num_actions, size=(cx.max_length, 1))
+            cx.action[0, 0] = int(RNG.rng.integers(self.num_actions, size=(cx.max_length, 1))[0, 0])
         if self.train_mode == TrainMode.TRAIN:
             self.replay_buffer.store_obs(obs)
 
@@ -267,6 +272,7 @@ class DtqnAgent:
         o = torch.as_tensor(np.asarray(obs, dtype=np.float64), device=self.device)
         o = torch.trunc(o) if cx.trunc_obs else o
         cx.obs[0, self._host_t % cx.max_length] = o.float()
+        cx.action[0, self._host_t % cx.max_length] = int(action)                 # utils/context.py:77
         cx.timestep_t.fill_(self._host_t)
         if self.train_mode == TrainMode.TRAIN:
             self.replay_buffer.store(obs, action, reward, done, self._host_t)

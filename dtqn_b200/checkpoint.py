@@ -252,7 +252,11 @@ def load_agent(agent, checkpoint_dir: str, validate=None):
         RNG.rng.bit_generator.state = ck["rng_bit_generator_state"]
     np.random.set_state(ck["numpy_rng_state"])
     torch.set_rng_state(ck["torch_rng_state"])
-    torch.cuda.set_rng_state(ck["torch_cuda_rng_state"], dev)
+    cuda_state = ck["torch_cuda_rng_state"]
+    if cuda_state.numel() == torch.cuda.get_rng_state(dev).numel():
+        torch.cuda.set_rng_state(cuda_state, dev)
+    # else: written on a CUDA-less host, where the reference stores the CPU generator state under this key (dqn.py:266-268);
+    # nothing on this path draws from torch's CUDA generator, so there is nothing to restore
     b = ck.get("b200")
     if b is not None:
         agent.stats_ring.copy_(b["stats_ring"])

@@ -67,7 +67,10 @@ __device__ __forceinline__ void ctx_write(const dtqn_context& cx, int i, int row
 // Context.reset (utils/context.py:36-54): fresh window with obs[0] = o; draws ctx bounded ints from the agent
 // stream for the (unused, a_embed = 0) random action padding so the stream stays aligned with the reference.
 __device__ __forceinline__ void ctx_reset(const dtqn_context& cx, int i, const float* o, int O, Pcg64& ag, unsigned A) {
-    for (int k = 0; k < cx.context_len; ++k) (void)ag.bounded(A);
+    for (int k = 0; k < cx.context_len; ++k) {
+        const unsigned a = ag.bounded(A);
+        if (k == 0 && cx.action) cx.action[(size_t)i * cx.context_len] = (uint8_t)a;
+    }
     cx.timestep[i] = 0;
     ctx_write(cx, i, 0, o, O);
 }
@@ -232,6 +235,7 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
             const int ts = cx.timestep[i] + 1;
             cx.timestep[i] = ts;
             ctx_write(cx, i, ts % cx.context_len, o, O);
+            if (cx.action) cx.action[(size_t)i * cx.context_len + ts % cx.context_len] = (uint8_t)a;   // context.py:77
         }
         if (done) {
             if (e.env_acc) {

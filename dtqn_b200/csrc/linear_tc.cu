@@ -1087,6 +1087,7 @@ extern "C" int64_t dtqn_packed_bytes(const dtqn_net_cfg* cfg) {
     NetLayout lay;
     int rc = net_layout(*cfg, lay);
     if (rc) return rc;
+    if (cfg_is_variant(*cfg)) return 16;          // ablation-flag networks run the fp32 path of net_var.cu: no operand image
     TcPackTable tab;
     tc_pack_table(*cfg, lay, tab);
     return tab.total_bytes;
@@ -1097,6 +1098,7 @@ extern "C" int dtqn_pack_weights(const dtqn_net_cfg* cfg, const float* params, v
     NetLayout lay;
     int rc = net_layout(*cfg, lay);
     if (rc) return rc;
+    if (cfg_is_variant(*cfg)) return 0;
     TcPackTable tab;
     tc_pack_table(*cfg, lay, tab);
     dim3 grid(16, tab.n);

@@ -10,11 +10,14 @@
 struct LayerOff {
     long long ln1_w, ln1_b, ln2_w, ln2_b, in_w, in_b, out_w, out_b, f1_w, f1_b, f2_w, f2_b;
 };
+struct GateOff { long long w_r, u_r, w_z, b_z, u_z, w_g, u_g; };   // GRUGate (gates.py:13-18): six [d,d] matrices + w_z.bias
 struct NetLayout {
     long long emb_table;   // [vocab, e]   (discrete only, else -1)   obs_embedding.observation_embedding.0.weight
-    long long emb_w;       // [d, K_in]    ...observation_embedding(.2).weight
-    long long emb_b;       // [d]
+    long long emb_w;       // [d - action_dim, K_in]    ...observation_embedding(.2).weight
+    long long emb_b;       // [d - action_dim]
+    long long act_table;   // [A, action_dim]  action_embedding.embedding.0.weight (action_dim > 0, else -1)
     long long pos;         // [ctx, d]     position_embedding.position_encoding
+    GateOff gate[2];       // shared attention gate, shared mlp gate (gate_gru only)
     LayerOff layer[DTQN_MAX_LAYERS];
     long long h1_w, h1_b;  // ffn.0  [d,d], [d]
     long long h2_w, h2_b;  // ffn.2  [A,d], [A]
@@ -24,20 +27,30 @@ struct NetLayout {
 
 static inline long long al4(long long x) { return (x + 3) & ~3ll; }
 
+// any ablation flag: the general kernel-per-op path (net_var.cu) instead of the fused default-architecture kernels
+static inline bool cfg_is_variant(const dtqn_net_cfg& c) {
+    return c.action_dim > 0 || c.identity || c.gate_gru || c.dropout > 0.f;
+}
+
 static inline int net_layout(const dtqn_net_cfg& c, NetLayout& L) {
     if (c.n_layers < 1 || c.n_layers > DTQN_MAX_LAYERS) return DTQN_E_ARG;
-    if (c.d_model != 64 && c.d_model != 128) return DTQN_E_UNSUPPORTED;
+    if (cfg_is_variant(c)) {
+        if (c.d_model < 8 || c.d_model > 256 || c.d_model % 4) return DTQN_E_UNSUPPORTED;
+        if (c.action_dim < 0 || c.action_dim >= c.d_model || c.action_dim % 4) return DTQN_E_UNSUPPORTED;
+        if (c.dropout < 0.f || c.dropout >= 1.f || (c.dropout > 0.f && !c.dropout_state)) return DTQN_E_ARG;
+    } else if (c.d_model != 64 && c.d_model != 128) return DTQN_E_UNSUPPORTED;
     if (c.n_heads <= 0 || c.d_model % c.n_heads || (c.d_model / c.n_heads) > 32 || (c.d_model / c.n_heads) % 4)
         return DTQN_E_UNSUPPORTED;
     if (c.context_len < 1 || c.context_len > 128 || c.obs_dim < 1 || c.obs_dim > 16 || c.num_actions < 1 ||
         c.num_actions > 32) return DTQN_E_UNSUPPORTED;
     if (c.discrete && (c.vocab < 1 || c.vocab > 64 || c.embed_per_obs < 1 || c.embed_per_obs > 16)) return DTQN_E_UNSUPPORTED;
-    const long long d = c.d_model;
+    const long long d = c.d_model, d_obs = d - c.action_dim;
     long long o = 0;
     L.k_in = c.discrete ? c.obs_dim * c.embed_per_obs : c.obs_dim;
     if (c.discrete) { L.emb_table = o; o = al4(o + (long long)c.vocab * c.embed_per_obs); } else L.emb_table = -1;
-    L.emb_w = o; o = al4(o + d * L.k_in);
-    L.emb_b = o; o = al4(o + d);
+    L.emb_w = o; o = al4(o + d_obs * L.k_in);
+    L.emb_b = o; o = al4(o + d_obs);
+    if (c.action_dim > 0) { L.act_table = o; o = al4(o + (long long)c.num_actions * c.action_dim); } else L.act_table = -1;
     L.pos = o;   o = al4(o + (long long)c.context_len * d);
     for (int i = 0; i < c.n_layers; ++i) {
         LayerOff& l = L.layer[i];
@@ -46,6 +59,13 @@ static inline int net_layout(const dtqn_net_cfg& c, NetLayout& L) {
         l.out_w = o; o += d * d;    l.out_b = o; o += d;
         l.f1_w = o; o += 4 * d * d; l.f1_b = o; o += 4 * d;
         l.f2_w = o; o += 4 * d * d; l.f2_b = o; o += d;
+        if (i == 0 && c.gate_gru) {
+            for (int k = 0; k < 2; ++k) {
+                GateOff& q = L.gate[k];
+                q.w_r = o; o += d * d; q.u_r = o; o += d * d; q.w_z = o; o += d * d; q.b_z = o; o += d;
+                q.u_z = o; o += d * d; q.w_g = o; o += d * d; q.u_g = o; o += d * d;
+            }
+        }
     }
     L.h1_w = o; o += d * d; L.h1_b = o; o += d;
     L.h2_w = o; o = al4(o + (long long)c.num_actions * d);
@@ -109,6 +129,15 @@ struct LinArgs {
     float* st_save;        // (mean, rstd) [G*Tg, 2] (nullable)
 };
 
+
+// ablation-flag networks (net_var.cu): general fp32 kernel-per-op forward / backward
+long long var_workspace_floats(const dtqn_net_cfg& c, long long T);
+int var_forward(const dtqn_net_cfg& c, const NetLayout& lay, int G, const float* const* params, const dtqn_obs_src* src,
+                int n_seq, int L, int q_mode, int save, float* ws, long long ws_floats, float* q_out, cudaStream_t st);
+long long var_bwd_scratch_floats(const dtqn_net_cfg& c, long long T0);
+int var_td_backward(const dtqn_net_cfg& c, const NetLayout& lay, const float* params, const dtqn_obs_src* obs_src,
+                    const float* dq, int B, int L, float* ws, long long ws_floats, float* scratch, float* grads,
+                    cudaStream_t st);
 
 // sequence-resident fused forward (net_seq.cu)
 bool seq_forward_supported(const dtqn_net_cfg& c, int L);

@@ -7,6 +7,27 @@
 
 namespace {
 
+// ---- deterministic cross-CTA sums -------------------------------------------------------------------------------------------
+// Every parameter gradient is a sum over tokens that several CTAs ("chunks") share.  Instead of fp32 atomics (run-to-run
+// order) each CTA stores its partial sums, takes a ticket, and the CTA that arrives LAST adds the partials of all chunks
+// in chunk order and writes the gradient: the value never depends on scheduling, so a step is bit-reproducible (eager ==
+// CUDA-graph replay == another run), like the reference's single-threaded-order autograd is.
+// Call with all threads of the CTA after the partial stores; returns true in every thread of the last CTA.
+__device__ __forceinline__ bool last_chunk_arrived(unsigned* ticket, unsigned n_chunks) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(ticket, 1u) == n_chunks - 1;
+        if (last) *ticket = 0u;                       // self-resetting: the next launch (stream-ordered) starts from 0
+        s_last = last;
+    }
+    __syncthreads();
+    const bool last = s_last;
+    if (last) __threadfence();
+    return last;
+}
+
 // ---- TD loss: emits dLoss/dQ directly + the logged statistics (agents/dtqn.py:245-253) --------------------------------
 // q_all [3, B, L, A]: 0 = policy(obs), 1 = policy(next_obs), 2 = target(next_obs).
 __global__ void __launch_bounds__(256)
@@ -73,12 +94,13 @@ td_loss_kernel(const float* __restrict__ q_all, const uint8_t* __restrict__ act_
 }
 
 // ---- head (ffn.2) backward: N = A is tiny -> CUDA cores --------------------------------------------------------------------
-// d_hh = (dq W2) * [hh > 0];  dW2 += dq^T hh;  db2 += colsum(dq).   HB_TOK tokens per CTA (few CTAs on purpose: the fp32 atomics into
-// gW2 are the least reproducible part of the update, and Q -- hence the greedy action -- reads W2 directly).
+// d_hh = (dq W2) * [hh > 0];  dW2 = dq^T hh;  db2 = colsum(dq).   HB_TOK tokens per CTA; per-CTA partials [A*d + A] summed in
+// CTA order by the last CTA.
 #define HB_TOK 64
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, const float* __restrict__ W2, int T, int d,
-                int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2) {
+                int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2,
+                float* __restrict__ part, unsigned* __restrict__ ticket) {
     __shared__ float sdq[HB_TOK][33];
     const int t0 = blockIdx.x * HB_TOK;
     const int nt = min(HB_TOK, T - t0);
@@ -98,12 +120,18 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, cons
         const int a = e / d, c = e % d;
         float s = 0.f;
         for (int r = 0; r < nt; ++r) s = fmaf(sdq[r][a], hh[(long long)(t0 + r) * d + c], s);
-        atomicAdd(gW2 + a * d + c, s);
+        part[(size_t)blockIdx.x * (A * d + A) + e] = s;
     }
     if (threadIdx.x < A) {
         float s = 0.f;
         for (int r = 0; r < nt; ++r) s += sdq[r][threadIdx.x];
-        atomicAdd(gb2 + threadIdx.x, s);
+        part[(size_t)blockIdx.x * (A * d + A) + A * d + threadIdx.x] = s;
+    }
+    if (!last_chunk_arrived(ticket, gridDim.x)) return;
+    for (int e = threadIdx.x; e < A * d + A; e += blockDim.x) {
+        float s = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (size_t)b * (A * d + A) + e);
+        if (e < A * d) gW2[e] = s; else gb2[e - A * d] = s;
     }
 }
 
@@ -139,14 +167,16 @@ dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const fl
     }
 }
 
-// ---- wgrad:  gW[Nf, Kf] += dY[T, Nf]^T X[T, Kf];  gb[Nf] += colsum(dY) --------------------------------------------------------
-// 64 x 64 tile of gW per CTA, tokens split over gridDim.z chunks, fp32 atomics into the (zeroed) flat gradient.
+// ---- wgrad:  gW[Nf, Kf] = dY[T, Nf]^T X[T, Kf];  gb[Nf] = colsum(dY) ----------------------------------------------------------
+// 64 x 64 tile of gW per CTA, tokens split over gridDim.z chunks (split-K); chunk partials go to pW / pb (same indexing as
+// gW / gb, `pstride` floats between chunks) and the last CTA of a tile adds them in chunk order.
 #define WG_CHUNK 64
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int Nf, int Kf,
-             float* __restrict__ gW, float* __restrict__ gb) {
-    __shared__ float As[16][64 + 4];   // dY slab: 16 tokens x 64 n
-    __shared__ float Bs[16][64 + 4];   // X  slab: 16 tokens x 64 k
+             float* __restrict__ gW, float* __restrict__ gb, float* __restrict__ pW, float* __restrict__ pb,
+             long long pstride, unsigned* __restrict__ tickets) {
+    __shared__ __align__(16) float As[16][64 + 4];   // dY slab: 16 tokens x 64 n   (float4 accesses: keep 16-byte aligned
+    __shared__ __align__(16) float Bs[16][64 + 4];   // X  slab: 16 tokens x 64 k    whatever else lives in static shared memory)
     const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
     const int tb = blockIdx.z * WG_CHUNK, te = min(T, tb + WG_CHUNK);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -180,11 +210,29 @@ wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, i
         }
         __syncthreads();
     }
+    const size_t poff = (size_t)blockIdx.z * pstride;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(pW + poff + (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    const bool do_bias = gb && blockIdx.y == 0;
+    if (do_bias && tid < 64) pb[poff + n0 + tid] = bsum;
+    if (!last_chunk_arrived(tickets + blockIdx.y * gridDim.x + blockIdx.x, gridDim.z)) return;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(gW + (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4 + j, acc[i][j]);
-    if (gb && blockIdx.y == 0 && tid < 64) atomicAdd(gb + n0 + tid, bsum);
+    for (int i = 0; i < 4; ++i) {
+        const size_t o = (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned z = 0; z < gridDim.z; ++z) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(pW + (size_t)z * pstride + o));
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        *reinterpret_cast<float4*>(gW + o) = sum;
+    }
+    if (do_bias && tid < 64) {
+        float sum = 0.f;
+        for (unsigned z = 0; z < gridDim.z; ++z) sum += __ldcg(pb + (size_t)z * pstride + n0 + tid);
+        gb[n0 + tid] = sum;
+    }
 }
 
 // ---- LayerNorm backward fused with the ReLU / residual split (transformer.py:72-73,76-77) -----------------------------------
@@ -193,7 +241,8 @@ template <int D>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xin, const float* __restrict__ r,
               const float* __restrict__ st, const float* __restrict__ gamma, int T, float* __restrict__ du,
-              float* __restrict__ da, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+              float* __restrict__ da, float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ part,
+              unsigned* __restrict__ ticket) {
     constexpr int PER = D / 32, ROWS = 4;                     // rows per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gam[PER], ag[PER], ab[PER];
@@ -231,7 +280,13 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xin, const
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         float s1 = 0.f, s2 = 0.f;
         for (int w = 0; w < 8; ++w) { s1 += sg[w][c]; s2 += sb[w][c]; }
-        atomicAdd(ggamma + c, s1); atomicAdd(gbeta + c, s2);
+        part[(size_t)blockIdx.x * 2 * D + c] = s1; part[(size_t)blockIdx.x * 2 * D + D + c] = s2;
+    }
+    if (!last_chunk_arrived(ticket, gridDim.x)) return;
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+        float sum = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * 2 * D + c);
+        if (c < D) ggamma[c] = sum; else gbeta[c - D] = sum;
     }
 }
 
@@ -338,14 +393,18 @@ __global__ void pos_bwd_kernel(const float* __restrict__ dx0, int B, int L, int 
 
 // obs embedding: continuous  gW[c,k] += sum_t dx0[t,c] obs[t,k];  discrete: through Embedding->Flatten->Linear.
 // 32 tokens per CTA.
+// Per-CTA partials [d*KI | d | vocab*E] summed in CTA order by the last CTA (no atomics; the table rows hit by several
+// tokens of a CTA are accumulated in token order).
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c, const float* __restrict__ params,
                  long long emb_table, long long emb_w, int L, int T, float* __restrict__ g_table,
-                 float* __restrict__ g_w, float* __restrict__ g_b) {
+                 float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ part, unsigned* __restrict__ ticket) {
     extern __shared__ float smem[];
     const int d = c.d_model, O = c.obs_dim, E = c.discrete ? c.embed_per_obs : 1, KI = O * E;
+    const int n_tab = c.discrete ? c.vocab * E : 0, n_part = d * KI + d + n_tab;
+    float* mypart = part + (size_t)blockIdx.x * n_part;
     float* sdx = smem;                 // [32][d]
-    float* sin_ = smem + 32 * d;       // [32][KI]  input features of the Linear (obs or looked-up embeddings)
+    float* sin_ = smem + 32 * d;       // [32][KI]  input features of the Linear (obs or looked-up embeddings); then d in[r, f]
     int* stok = reinterpret_cast<int*>(sin_ + 32 * KI);   // [32][O] token ids (discrete)
     const int t0 = blockIdx.x * 32, nt = min(32, T - t0);
     for (int e = threadIdx.x; e < 32 * d; e += blockDim.x) {
@@ -370,20 +429,39 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
         const int cc = e / KI, f = e % KI;
         float s = 0.f;
         for (int r = 0; r < nt; ++r) s = fmaf(sdx[r * d + cc], sin_[r * KI + f], s);
-        atomicAdd(g_w + e, s);
+        mypart[e] = s;
     }
     for (int cc = threadIdx.x; cc < d; cc += blockDim.x) {
         float s = 0.f;
         for (int r = 0; r < nt; ++r) s += sdx[r * d + cc];
-        atomicAdd(g_b + cc, s);
+        mypart[d * KI + cc] = s;
     }
     if (c.discrete) {
-        for (int e = threadIdx.x; e < nt * KI; e += blockDim.x) {     // d table[tok(r,k), ee] += sum_c dx[r,c] W[c, f]
+        __syncthreads();                                              // sin_ is reused for d in[r, f] = sum_c dx[r,c] W[c, f]
+        for (int e = threadIdx.x; e < 32 * KI; e += blockDim.x) {
             const int r = e / KI, f = e % KI;
             float s = 0.f;
-            for (int cc = 0; cc < d; ++cc) s = fmaf(sdx[r * d + cc], __ldg(params + emb_w + (long long)cc * KI + f), s);
-            atomicAdd(g_table + stok[r * O + f / E] * E + (f % E), s);
+            if (r < nt)
+                for (int cc = 0; cc < d; ++cc) s = fmaf(sdx[r * d + cc], __ldg(params + emb_w + (long long)cc * KI + f), s);
+            sin_[e] = s;
         }
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_tab; e += blockDim.x) {       // d table[v, ee] = sum over (r, k) with tok(r, k) == v
+            const int v = e / E, ee = e % E;
+            float s = 0.f;
+            for (int r = 0; r < nt; ++r)
+                for (int k = 0; k < O; ++k)
+                    if (stok[r * O + k] == v) s += sin_[r * KI + k * E + ee];
+            mypart[d * KI + d + e] = s;
+        }
+    }
+    if (!last_chunk_arrived(ticket, gridDim.x)) return;
+    for (int e = threadIdx.x; e < n_part; e += blockDim.x) {
+        float sum = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * n_part + e);
+        if (e < d * KI) g_w[e] = sum;
+        else if (e < d * KI + d) g_b[e - d * KI] = sum;
+        else g_table[e - d * KI - d] = sum;
     }
 }
 
@@ -428,11 +506,13 @@ int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, i
     return 0;
 }
 
-int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gW, float* gb, cudaStream_t st) {
-    if (Nf % 64 || Kf % 64) return DTQN_E_UNSUPPORTED;
+// pW / pb: chunk-partial areas of this weight / bias (same offsets as in the flat gradient), pstride floats between chunks
+int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gW, float* gb, float* pW, float* pb,
+                 long long pstride, unsigned* tickets, cudaStream_t st) {
+    if (Nf % 64 || Kf % 64 || (Nf / 64) * (Kf / 64) > 64) return DTQN_E_UNSUPPORTED;
     dim3 grid(Nf / 64, Kf / 64, dtqn_cdiv(T, WG_CHUNK));
     prof_begin(PROF_WGRAD, st);
-    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gW, gb);
+    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gW, gb, pW, pb, pstride, tickets);
     prof_end(PROF_WGRAD, st, 2.0 * (double)T * Nf * Kf);
     DTQN_LAUNCH_CHECK();
     return 0;
@@ -440,7 +520,9 @@ int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* 
 
 struct BwdScratch {
     float *dq, *g_hh, *gx, *gu, *ga, *ga1, *gh, *gqkv, *go, *gx1, *partial;
-    unsigned* ticket;
+    float *pgrad;            // [n_chunks][flat parameter count] split-K partials of the weight / bias gradients
+    float *psmall;           // per-CTA partials of the head / LayerNorm / embedding gradients (one launch at a time)
+    unsigned* ticket;        // [0] td loss; [1] head; [2] LayerNorm; [3] embedding; [8, 72) weight-gradient tiles
     long long total;
 };
 long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, BwdScratch& s) {
@@ -450,7 +532,15 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
     s.dq = take(T0 * c.num_actions); s.g_hh = take(T0 * d); s.gx = take(T0 * d); s.gu = take(T0 * d);
     s.ga = take(T0 * d); s.ga1 = take(T0 * d); s.gh = take(T0 * 4 * d); s.gqkv = take(T0 * 3 * d); s.go = take(T0 * d); s.gx1 = take(T0 * d);
     s.partial = take((long long)dtqn_cdiv(T0, 256) * 8);
-    s.ticket = reinterpret_cast<unsigned*>(take(4));
+    NetLayout lay;
+    net_layout(c, lay);
+    s.pgrad = take((long long)dtqn_cdiv(T0, WG_CHUNK) * lay.total);
+    const long long n_emb = d * lay.k_in + d + (c.discrete ? (long long)c.vocab * c.embed_per_obs : 0);
+    long long small = (long long)dtqn_cdiv(T0, HB_TOK) * (c.num_actions * d + c.num_actions);
+    if ((long long)dtqn_cdiv(T0, 32) * 2 * d > small) small = (long long)dtqn_cdiv(T0, 32) * 2 * d;
+    if ((long long)dtqn_cdiv(T0, 32) * n_emb > small) small = (long long)dtqn_cdiv(T0, 32) * n_emb;
+    s.psmall = take(small);
+    s.ticket = reinterpret_cast<unsigned*>(take(72));
     s.total = o;
     return o;
 }
@@ -461,8 +551,11 @@ extern "C" int dtqn_set_parallel_wgrad(int32_t on) { g_parallel_wgrad = on; retu
 
 extern "C" int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len) {
     if (!cfg || batch < 1 || seq_len < 1) return DTQN_E_ARG;
+    const long long T0 = (long long)batch * seq_len;
+    if (cfg_is_variant(*cfg))       // dq | td partials | ticket | scratch of net_var.cu
+        return al4(T0 * cfg->num_actions) + al4((long long)dtqn_cdiv(T0, 256) * 8) + 4 + var_bwd_scratch_floats(*cfg, T0);
     BwdScratch s;
-    return bwd_scratch_layout(*cfg, (long long)batch * seq_len, nullptr, s);
+    return bwd_scratch_layout(*cfg, T0, nullptr, s);
 }
 
 extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, const dtqn_obs_src* obs_src,
@@ -475,6 +568,21 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     int rc = net_layout(*cfg, lay);
     if (rc) return rc;
     const long long T0 = (long long)B * L, T = 3 * T0;
+    if (cfg_is_variant(*cfg)) {                                // ablation flags: TD loss here, backward in net_var.cu
+        cudaStream_t vst = (cudaStream_t)stream;
+        float* dq = scratch;
+        float* partial = dq + al4(T0 * cfg->num_actions);
+        unsigned* ticket = reinterpret_cast<unsigned*>(partial + al4((long long)dtqn_cdiv(T0, 256) * 8));
+        float* vscratch = reinterpret_cast<float*>(ticket) + 4;
+        cudaError_t ce = cudaMemsetAsync(grads, 0, sizeof(float) * lay.total, vst);
+        if (ce != cudaSuccess) return (int)ce;
+        prof_begin(PROF_TD, vst);
+        td_loss_kernel<<<dtqn_cdiv(T0, 256), 256, 0, vst>>>(q_all, act_win, rew, done, B, L, cfg->num_actions, history, gamma, dq,
+                                                             partial, ticket, stats_out);
+        prof_end(PROF_TD, vst, 0.0);
+        DTQN_LAUNCH_CHECK();
+        return var_td_backward(*cfg, lay, params, obs_src, dq, B, L, ws, ws_floats, vscratch, grads, vst);
+    }
     NetAct act;
     if (net_act_layout(*cfg, T, 1, ws, act) > ws_floats) return DTQN_E_ARG;
     BwdScratch s;
@@ -492,16 +600,21 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
     prof_begin(PROF_HEAD, st);
     head_bwd_kernel<<<dtqn_cdiv(T0, HB_TOK), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
-                                                        grads + lay.h2_w, grads + lay.h2_b);
+                                                        grads + lay.h2_w, grads + lay.h2_b, s.psmall, s.ticket + 1);
     prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();
     g_side.init();
     const bool par = g_parallel_wgrad && g_side.ok;
     cudaStream_t ws_ = par ? g_side.st : st;                       // stream of the weight-gradient GEMMs
     auto fork = [&]() { if (par) g_side.fork(st); };
+    // weight gradient of the Linear whose weight / bias sit at w_off / b_off of the flat layout (split-K, fixed-order sum)
+    auto wgrad = [&](const float* dY, const float* X, int Nf, int Kf, long long w_off, long long b_off) {
+        return launch_wgrad(dY, X, Ti, Nf, Kf, grads + w_off, grads + b_off, s.pgrad + w_off, s.pgrad + b_off, lay.total,
+                            s.ticket + 8, ws_);
+    };
     const float* x_last = act.layer[cfg->n_layers - 1].x2;
     fork();
-    if ((rc = launch_wgrad(s.g_hh, x_last, Ti, d, d, grads + lay.h1_w, grads + lay.h1_b, ws_))) return rc;
+    if ((rc = wgrad(s.g_hh, x_last, d, d, lay.h1_w, lay.h1_b))) return rc;
     if ((rc = launch_dgrad<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, s.gx, Ti, d, d, st))) return rc;
     for (int li = cfg->n_layers - 1; li >= 0; --li) {
         const LayerOff& lo = lay.layer[li];
@@ -509,27 +622,27 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         const float* x_in = li == 0 ? act.x0 : act.layer[li - 1].x2;
         // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
         prof_begin(PROF_LN_BWD, st);
-        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
-        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b);
+        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
+        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // ffn.2
         fork();
-        if ((rc = launch_wgrad(s.ga, la.h, Ti, d, 4 * d, grads + lo.f2_w, grads + lo.f2_b, ws_))) return rc;
+        if ((rc = wgrad(s.ga, la.h, d, 4 * d, lo.f2_w, lo.f2_b))) return rc;
         if ((rc = launch_dgrad<DG_MASK>(s.ga, params + lo.f2_w, la.h, s.gh, Ti, d, 4 * d, st))) return rc;
         // ffn.0
         fork();
-        if ((rc = launch_wgrad(s.gh, la.x1, Ti, 4 * d, d, grads + lo.f1_w, grads + lo.f1_b, ws_))) return rc;
+        if ((rc = wgrad(s.gh, la.x1, 4 * d, d, lo.f1_w, lo.f1_b))) return rc;
         if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
         // LN1 backward: dy = gx1 -> gu (du1), ga1 (d out_proj output)
         prof_begin(PROF_LN_BWD, st);
-        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b);
-        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b);
+        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
+        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // out_proj
         fork();
-        if ((rc = launch_wgrad(s.ga1, la.o, Ti, d, d, grads + lo.out_w, grads + lo.out_b, ws_))) return rc;
+        if ((rc = wgrad(s.ga1, la.o, d, d, lo.out_w, lo.out_b))) return rc;
         if ((rc = launch_dgrad<DG_NONE>(s.ga1, params + lo.out_w, nullptr, s.go, Ti, d, d, st))) return rc;
         // attention core
         {
@@ -546,7 +659,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         }
         // in_proj
         fork();
-        if ((rc = launch_wgrad(s.gqkv, x_in, Ti, 3 * d, d, grads + lo.in_w, grads + lo.in_b, ws_))) return rc;
+        if ((rc = wgrad(s.gqkv, x_in, 3 * d, d, lo.in_w, lo.in_b))) return rc;
         if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
         if (par) g_side.join(st);          // the next layer overwrites ga / gh / gqkv / ga1
     }
@@ -561,7 +674,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         const size_t smem = sizeof(float) * (32 * d + 32 * KI) + sizeof(int) * 32 * cfg->obs_dim;
         embed_bwd_kernel<<<dtqn_cdiv(T0, 32), 256, smem, st>>>(s.gx, *obs_src, *cfg, params, lay.emb_table, lay.emb_w, L, Ti,
                                                               cfg->discrete ? grads + lay.emb_table : nullptr,
-                                                              grads + lay.emb_w, grads + lay.emb_b);
+                                                              grads + lay.emb_w, grads + lay.emb_b, s.psmall, s.ticket + 3);
         DTQN_LAUNCH_CHECK();
     }
     prof_end(PROF_OTHER, st, 0.0);

@@ -647,11 +647,18 @@ extern "C" int dtqn_net_param_offsets(const dtqn_net_cfg* cfg, int64_t* out, int
     int n = 0;
     auto put = [&](long long v) { if (n < max_entries) out[n] = v; ++n; };
     if (cfg->discrete) put(L.emb_table);
-    put(L.emb_w); put(L.emb_b); put(L.pos);
+    put(L.emb_w); put(L.emb_b);
+    if (cfg->action_dim > 0) put(L.act_table);
+    put(L.pos);
     for (int i = 0; i < cfg->n_layers; ++i) {
         const LayerOff& l = L.layer[i];
         put(l.ln1_w); put(l.ln1_b); put(l.ln2_w); put(l.ln2_b); put(l.in_w); put(l.in_b); put(l.out_w); put(l.out_b);
         put(l.f1_w); put(l.f1_b); put(l.f2_w); put(l.f2_b);
+        if (i == 0 && cfg->gate_gru)
+            for (int k = 0; k < 2; ++k) {
+                const GateOff& q = L.gate[k];
+                put(q.w_r); put(q.u_r); put(q.w_z); put(q.b_z); put(q.u_z); put(q.w_g); put(q.u_g);
+            }
     }
     put(L.h1_w); put(L.h1_b); put(L.h2_w); put(L.h2_b);
     return n > max_entries ? DTQN_E_ARG : n;
@@ -659,6 +666,7 @@ extern "C" int dtqn_net_param_offsets(const dtqn_net_cfg* cfg, int64_t* out, int
 
 extern "C" int64_t dtqn_net_workspace_floats(const dtqn_net_cfg* cfg, int64_t n_tokens, int32_t save) {
     if (!cfg || n_tokens <= 0) return DTQN_E_ARG;
+    if (cfg_is_variant(*cfg)) return var_workspace_floats(*cfg, n_tokens);
     NetAct A;
     return net_act_layout(*cfg, n_tokens, save, nullptr, A);
 }
@@ -685,10 +693,17 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
     NetLayout lay;
     int rc = net_layout(*cfg, lay);
     if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg_is_variant(*cfg)) {                                // ablation flags: general fp32 kernel-per-op path
+        for (int g = 0; g < G; ++g) {
+            if (!params[g] || !src[g].obs) return DTQN_E_ARG;
+            if (src[g].timestep && src[g].ring_len < L) return DTQN_E_ARG;
+        }
+        return var_forward(*cfg, lay, G, params, src, n_seq, L, q_mode, save, ws, ws_floats, q_out, st);
+    }
     const long long Tg = (long long)n_seq * L, T = Tg * G;
     NetAct act;
     if (net_act_layout(*cfg, T, save, ws, act) > ws_floats) return DTQN_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     const int d = cfg->d_model, H = cfg->n_heads, hd = d / H;
     GroupPtrs P{}; GroupSrc S{};
     const uint8_t* pk[DTQN_MAX_GROUPS] = {nullptr, nullptr, nullptr};

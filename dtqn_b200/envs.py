@@ -157,10 +157,12 @@ class ContextWindow:
         self.env_obs_length, self.n_envs, self.device = int(env_obs_length), int(n_envs), dev
         self.obs = torch.full((n_envs, context_len, env_obs_length), float(obs_mask), dtype=torch.float32, device=dev)
         self.timestep_t = torch.zeros(n_envs, dtype=torch.int32, device=dev)
+        self.action = torch.zeros((n_envs, context_len), dtype=torch.uint8, device=dev)     # Context.action ring (a_embed > 0)
         self.trunc_obs = bool(trunc_obs)
         self.struct = _lib.ContextStruct(context_len=self.max_length, obs_dim=self.env_obs_length,
                                          trunc_obs=int(self.trunc_obs), obs_mask=self.obs_mask,
-                                         obs=_lib.ptr(self.obs), timestep=_lib.ptr(self.timestep_t))
+                                         obs=_lib.ptr(self.obs), timestep=_lib.ptr(self.timestep_t),
+                                         action=_lib.ptr(self.action))
 
     @property
     def timestep(self) -> int:

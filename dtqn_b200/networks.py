@@ -17,12 +17,15 @@ from dtqn_b200 import _lib
 
 class NetCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("obs_dim", "num_actions", "d_model", "n_heads", "n_layers", "context_len",
-                                         "discrete", "vocab", "embed_per_obs", "pos_trainable")]
+                                         "discrete", "vocab", "embed_per_obs", "pos_trainable",
+                                         "action_dim", "identity", "gate_gru")] + [("dropout", C.c_float),
+                                                                                    ("dropout_state", C.c_void_p)]
 
 
 class ObsSrc(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("seq_stride", C.c_int64), ("timestep", C.c_void_p), ("ring_len", C.c_int32),
-                ("obs_mask", C.c_float)]
+                ("obs_mask", C.c_float), ("actions", C.c_void_p), ("act_stride", C.c_int64), ("train_mode", C.c_int32),
+                ("_pad", C.c_int32)]
 
 
 _l = _lib.lib
@@ -69,18 +72,15 @@ class DTQN(nn.Module):
             raise ValueError("Gate must be one of `gru`, `res`")            # dtqn.py:113-114
         if pos not in ("learned", "sin", "none"):
             raise ValueError(f"{pos!r} is not a valid PosEnum")             # dtqn.py:101 (PosEnum(pos))
-        unsupported = []
-        if action_dim: unsupported.append("--a-embed > 0")
-        if dropout: unsupported.append("--dropout > 0")
-        if gate != "res": unsupported.append("--gate gru")
-        if identity: unsupported.append("--identity")
-        if bag_size: unsupported.append("--bag-size > 0")
-        if unsupported:
-            raise NotImplementedError("not on the B200 hot path yet (SURVEY.md section 8f rank 3): " + ", ".join(unsupported))
+        if bag_size:
+            raise NotImplementedError("DTQN-bag (--bag-size > 0) is outside the hot path (SURVEY.md section 2 #23)")
         dev = _lib.require_cuda(device)
         self.obs_dim, self.num_actions, self.discrete = int(obs_dim), int(num_actions), bool(discrete)
         self.history_len, self.num_heads, self.num_layers = int(history_len), int(num_heads), int(num_layers)
         self.inner_embed_size, self.pos_kind, self.bag_size = int(inner_embed_size), pos, 0
+        self.action_dim, self.identity, self.gate_kind, self.dropout_p = int(action_dim), bool(identity), gate, float(dropout)
+        # mask-stream counter of the dropout kernels (device scalar: CUDA-graph replays advance it without host writes)
+        self.dropout_state = torch.zeros(1, dtype=torch.int64, device=dev)
         vocab = int(np.max(vocab_sizes)) if (discrete and vocab_sizes is not None) else 0
         if discrete:
             assert vocab > 0, "Discrete environments need to have a vocab size for the token embeddings"
@@ -88,7 +88,9 @@ class DTQN(nn.Module):
         self.cfg = NetCfg(obs_dim=self.obs_dim, num_actions=self.num_actions, d_model=self.inner_embed_size,
                           n_heads=self.num_heads, n_layers=self.num_layers, context_len=self.history_len,
                           discrete=int(self.discrete), vocab=vocab, embed_per_obs=int(embed_per_obs_dim) if discrete else 0,
-                          pos_trainable=int(pos == "learned"))
+                          pos_trainable=int(pos == "learned"), action_dim=self.action_dim, identity=int(self.identity),
+                          gate_gru=int(gate == "gru"), dropout=self.dropout_p,
+                          dropout_state=self.dropout_state.data_ptr() if self.dropout_p > 0 else None)
         n = _l.dtqn_net_param_count(C.byref(self.cfg))
         if n < 0:
             raise ValueError(f"unsupported DTQN configuration for the sm_100a kernels (code {n})")
@@ -139,13 +141,19 @@ class DTQN(nn.Module):
             seq = _Holder()
             e0, e2 = _Holder(), _Holder()
             e0.weight = self._view((V, E))
-            e2.weight = self._view((d, O * E)); e2.bias = self._view((d,))
+            e2.weight = self._view((d - self.action_dim, O * E)); e2.bias = self._view((d - self.action_dim,))
             seq.add_module("0", e0); seq.add_module("2", e2)
             self.obs_embedding.observation_embedding = seq
         else:
             lin = _Holder()
-            lin.weight = self._view((d, O)); lin.bias = self._view((d,))
+            lin.weight = self._view((d - self.action_dim, O)); lin.bias = self._view((d - self.action_dim,))
             self.obs_embedding.observation_embedding = lin
+        if self.action_dim > 0:                                                # representations.py:146-155
+            self.action_embedding = _Holder()
+            seq = _Holder(); a0 = _Holder()
+            a0.weight = self._view((A, self.action_dim))
+            seq.add_module("0", a0)
+            self.action_embedding.embedding = seq
         self.position_embedding = _Holder()
         self.position_embedding.position_encoding = self._view((1, ctx, d), trainable=self.pos_kind == "learned")
         self.transformer_layers = _Holder()
@@ -164,6 +172,18 @@ class DTQN(nn.Module):
             f0.weight = self._view((4 * d, d)); f0.bias = self._view((4 * d,))
             f2.weight = self._view((d, 4 * d)); f2.bias = self._view((d,))
             blk.ffn.add_module("0", f0); blk.ffn.add_module("2", f2)
+            if self.gate_kind == "gru":          # ONE attention gate and ONE mlp gate shared by every layer (dtqn.py:107-131)
+                if i == 0:
+                    gates = []
+                    for _ in range(2):           # gates.py:13-18; w_z.bias = -2 (:22-24) is set by _init_weights
+                        g = _Holder()
+                        for nm in ("w_r", "u_r", "w_z", "u_z", "w_g", "u_g"):
+                            setattr(g, nm, _Holder())
+                        g.w_r.weight = self._view((d, d)); g.u_r.weight = self._view((d, d))
+                        g.w_z.weight = self._view((d, d)); g.w_z.bias = self._view((d,))
+                        g.u_z.weight = self._view((d, d)); g.w_g.weight = self._view((d, d)); g.u_g.weight = self._view((d, d))
+                        gates.append(g)
+                blk.attn_gate, blk.mlp_gate = gates
             self.transformer_layers.add_module(str(i), blk)
         self.ffn = _Holder()
         h0, h2 = _Holder(), _Holder()
@@ -183,6 +203,8 @@ class DTQN(nn.Module):
                 p.copy_(_sinusoid(self.history_len, self.inner_embed_size) if self.pos_kind == "sin" else torch.zeros_like(p))
             elif "layernorm" in name:
                 p.fill_(1.0 if name.endswith("weight") else 0.0)
+            elif name.endswith("w_z.bias"):
+                p.fill_(-2.0)                                                  # GTrXL gate bias (gates.py:22-24)
             elif name.endswith("bias"):
                 p.zero_()
             else:
@@ -215,7 +237,12 @@ class DTQN(nn.Module):
         assert O == self.obs_dim, f"Obs dim is incorrect. Expected {self.obs_dim} got {O}"          # dtqn.py:177-179
         x = obss.to(device=self.flat.device, dtype=torch.float32).contiguous()
         q = torch.empty((B, L, self.num_actions), dtype=torch.float32, device=self.flat.device)
-        src = ObsSrc(obs=x.data_ptr(), seq_stride=L * O, timestep=None, ring_len=0, obs_mask=0.0)
+        act = None
+        if self.action_dim > 0:                                                # dtqn.py:184-192
+            assert actions is not None, "a network built with action_dim > 0 needs the actions"
+            act = actions.to(device=self.flat.device).reshape(B, L).to(torch.uint8).contiguous()
+        src = ObsSrc(obs=x.data_ptr(), seq_stride=L * O, timestep=None, ring_len=0, obs_mask=0.0,
+                     actions=act.data_ptr() if act is not None else None, act_stride=L, train_mode=int(self.training))
         forward_groups(self, [self], [src], B, L, q_mode=0, save=0, q_out=q)
         return q
 

@@ -64,12 +64,8 @@ def run_experiment(args):
     from dtqn_b200.runner import BatchedTrainer
     if len(args.envs) != 1:
         raise NotImplementedError("multi-env sampling needs identical spaces (run.py:47); run one trainer per env id")
-    for flag, bad in (("--a-embed", args.a_embed), ("--dropout", args.dropout), ("--identity", args.identity),
-                      ("--bag-size", args.bag_size)):
-        if bad:
-            raise NotImplementedError(f"{flag} is not on the B200 hot path yet (DESIGN.md section 7)")
-    if args.gate != "res":
-        raise NotImplementedError("--gate gru is not on the B200 hot path yet (DESIGN.md section 7)")
+    if args.bag_size:
+        raise NotImplementedError("--bag-size > 0 (DTQN-bag) is outside the hot path (SURVEY.md section 2 #23)")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
@@ -81,7 +77,8 @@ def run_experiment(args):
                         heads=args.heads, layers=args.layers, context=args.context, batch=args.batch,
                         buf_size=max(args.buf_size, 8 * args.n_envs * 200), lr=args.lr, tuf=args.tuf,
                         gamma=args.discount, history=args.history, num_steps=args.num_steps, obs_embed=args.obs_embed,
-                        pos=args.pos, max_episode_steps=args.max_episode_steps)
+                        pos=args.pos, max_episode_steps=args.max_episode_steps, a_embed=args.a_embed, dropout=args.dropout,
+                        identity=args.identity, gate=args.gate)
     rank = tr.rank
     if rank == 0:
         n = sum(p.numel() for p in tr.agent.policy_network.parameters())

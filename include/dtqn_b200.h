@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DTQN_ABI_VERSION 4
+#define DTQN_ABI_VERSION 5
 
 #define DTQN_E_ARG      (-1)  /* null pointer / out-of-range size */
 #define DTQN_E_UNSUPPORTED (-2)
@@ -89,7 +89,7 @@ typedef struct dtqn_replay {
     int32_t* env_prev_len;      /* [n_envs] length of the episode previously stored in the env's open slot */
 } dtqn_replay;
 
-/* ---- acting history: utils/context.py:8-111 (obs window only; a_embed = 0 so the action window is unused) ------- */
+/* ---- acting history: utils/context.py:8-111 (obs window; the action window only feeds --a-embed > 0 networks) ------- */
 typedef struct dtqn_context {
     int32_t context_len;
     int32_t obs_dim;
@@ -97,6 +97,9 @@ typedef struct dtqn_context {
     float   obs_mask;
     float*   obs;               /* [n_envs, ctx, O] ring; token j of the window = ring[(t+1-n+j) % ctx] */
     int32_t* timestep;          /* [n_envs] Context.timestep */
+    uint8_t* action;            /* nullable [n_envs, ctx] ring of Context.action (utils/context.py:50,77): row t % ctx = the
+                                   action that led to the observation of timestep t; row 0 of a fresh context = the first of
+                                   the ctx random padding actions Context.reset draws (the only one a window can ever show) */
 } dtqn_context;
 
 typedef struct dtqn_step_io {
@@ -158,6 +161,17 @@ typedef struct dtqn_net_cfg {
     int32_t vocab;          /* discrete only: obs_mask + 1 (utils/agent_utils.py:92-95) */
     int32_t embed_per_obs;  /* discrete only: e */
     int32_t pos_trainable;  /* 1 = learned position table (gets a gradient), 0 = sin / none (still added) */
+    /* ---- ablation flags of run.py:98-103,151-167 (all 0 = the default architecture and its fused kernels); any of them
+     *      selects the general fp32 kernel-per-op path of csrc/net_var.cu ---- */
+    int32_t action_dim;     /* --a-embed: width of the previous-action embedding concatenated IN FRONT of the observation
+                               embedding, which then has d_model - action_dim columns (dtqn.py:64-71,184-192) */
+    int32_t identity;       /* --identity: TransformerIdentityLayer, LayerNorm before each sub-layer (transformer.py:81-101) */
+    int32_t gate_gru;       /* --gate gru: GRUGate (gates.py:5-31); ONE attention gate and ONE mlp gate shared by all layers
+                               (dtqn.py:107-131), so their gradients sum over layers */
+    float   dropout;        /* --dropout p: token embedding (dtqn.py:195-199), attention probabilities (nn.MultiheadAttention,
+                               transformer.py:31-36) and the FFN output (transformer.py:41); train-mode groups only */
+    uint64_t* dropout_state; /* device uint64[1], required when dropout > 0: mask stream counter (advanced once per acting
+                               forward and once per training step; the backward regenerates the forward's masks from it) */
 } dtqn_net_cfg;
 
 /* Where a group of sequences reads its observations.  Sequence i, token j reads row
@@ -169,11 +183,18 @@ typedef struct dtqn_obs_src {
     const int32_t* timestep;     /* nullable */
     int32_t        ring_len;
     float          obs_mask;     /* value of context rows not yet written (Context.reset fill, utils/context.py:46): -5 | 8 */
+    const uint8_t* actions;      /* action_dim > 0 only: action of token j at actions + i * act_stride + j (same ring indexing
+                                    as obs when timestep != NULL); token j is embedded with the action of token j - 1 */
+    int64_t        act_stride;
+    int32_t        train_mode;   /* 1: this group's network is in train() mode (dropout active); 0: eval() (target network) */
+    int32_t        _pad;
 } dtqn_obs_src;
 
 /* Number of floats of the flat parameter buffer, and the offset of every tensor in it, in this fixed order:
- *   [emb_table (discrete only)], emb_w, emb_b, pos, then per layer: ln1_w, ln1_b, ln2_w, ln2_b, in_w, in_b, out_w,
- *   out_b, f1_w, f1_b, f2_w, f2_b, then h1_w, h1_b, h2_w, h2_b.   Returns the tensor count (or < 0). */
+ *   [emb_table (discrete only)], emb_w, emb_b, [act_table (action_dim > 0)], pos, then per layer: ln1_w, ln1_b, ln2_w,
+ *   ln2_b, in_w, in_b, out_w, out_b, f1_w, f1_b, f2_w, f2_b -- with the two shared GRU gates right after layer 0 when
+ *   gate_gru (attention gate then mlp gate, each w_r, u_r, w_z, b_z, u_z, w_g, u_g) -- then h1_w, h1_b, h2_w, h2_b.
+ *   Returns the tensor count (or < 0). */
 int64_t dtqn_net_param_count(const dtqn_net_cfg* cfg);
 int dtqn_net_param_offsets(const dtqn_net_cfg* cfg, int64_t* offsets_out, int32_t max_entries);
 /* Floats of activation workspace for n_tokens = groups * n_seq * seq_len tokens. */
@@ -188,6 +209,11 @@ int dtqn_forward(const dtqn_net_cfg* cfg, int32_t n_groups, const float* const* 
                  const void* const* packed /* nullable: per-group dtqn_pack_weights images -> tcgen05 GEMMs */,
                  const dtqn_obs_src* src, int32_t n_seq, int32_t seq_len, int32_t q_mode, int32_t save, float* workspace,
                  int64_t workspace_floats, float* q_out, void* stream);
+
+/* Measurement / test hook for --dropout: the keep-scale (0 or 1 / (1 - p)) the dropout kernels apply to element idx = 0..n-1
+ * of mask site `site` (1 token embedding, 2 + 4 l attention probabilities of layer l, 3 + 4 l FFN output of layer l) when the
+ * mask-stream counter (cfg.dropout_state[0]) holds `counter`. */
+int dtqn_dropout_scales(uint64_t counter, uint32_t site, float p, int64_t n, float* out, void* stream);
 
 /* tcgen05 operand images of the GEMM weights (in_proj / out_proj / ffn.0 / ffn.2 per layer + head ffn.0): each weight
  * split into bf16 hi + lo and tiled in the K-major shared-memory layout the tensor core reads, so the kernel fetches a

@@ -12,17 +12,18 @@ import torch
 from oracle import network
 
 
-def td_loss(policy_sd, target_sd, batch, num_heads, gamma=0.99, history=None):
+def td_loss(policy_sd, target_sd, batch, num_heads, gamma=0.99, history=None, identity=False):
     """dtqn.py:215-243.  ``batch`` = (obss, actions, rewards, next_obss, next_actions, dones) as returned by
     ReplayBuffer.sample.  Returns (loss, q_sel[B,H], targets[B,H]); loss carries autograd history w.r.t. policy_sd.
     Padded positions are NOT masked."""
-    obss, actions, rewards, next_obss, _next_actions, dones = batch
+    obss, actions, rewards, next_obss, next_actions, dones = batch
     actions = actions.long()
-    q = network.forward(policy_sd, obss, num_heads)                      # :215
+    fw = lambda sd, o, a: network.forward(sd, o, num_heads, actions=a, identity=identity)   # actions only feed --a-embed nets
+    q = fw(policy_sd, obss, actions)                                     # :215
     q = q.gather(2, actions).squeeze(-1)                                 # :219
     with torch.no_grad():
-        a_star = network.forward(policy_sd, next_obss, num_heads).argmax(dim=2, keepdim=True)   # :226-229
-        q_next = network.forward(target_sd, next_obss, num_heads).gather(2, a_star).squeeze(-1)  # :230-233
+        a_star = fw(policy_sd, next_obss, next_actions).argmax(dim=2, keepdim=True)             # :226-229
+        q_next = fw(target_sd, next_obss, next_actions).gather(2, a_star).squeeze(-1)            # :230-233
         y = rewards.squeeze(-1) + (1 - dones.long().squeeze(-1)) * (q_next * gamma)            # :236-238
     h = history or q.shape[1]
     q, y = q[:, -h:], y[:, -h:]                                          # :240-241
@@ -47,24 +48,38 @@ def adam_step(p, g, m, v, t, lr=3e-4, b1=0.9, b2=0.999, eps=1e-8):
     return p, m, v
 
 
+def _gate_base(key: str) -> str:
+    import re
+    return re.sub(r"transformer_layers\.\d+\.(attn_gate|mlp_gate)", r"transformer_layers.0.\1", key)
+
+
 class TrainerOracle:
     """Holds policy/target state dicts + Adam moments and performs DtqnAgent.train() on a given batch."""
 
     def __init__(self, sd, num_heads, pos="learned", lr=3e-4, gamma=0.99, grad_norm_clip=1.0,
-                 target_update_frequency=10_000, history=None):
+                 target_update_frequency=10_000, history=None, identity=False):
+        self.identity = identity
         self.policy = {k: v.clone() for k, v in sd.items()}
         self.target = {k: v.clone() for k, v in sd.items()}             # dqn.py:46-50
-        self.keys = network.trainable_keys(sd, pos)
+        # GRU gates are ONE module shared by all layers (dtqn.py:107-131): the state_dict repeats them per layer; only the
+        # layer-0 entry is a leaf, the others alias it so autograd sums the layers' contributions
+        self.tied = {k: _gate_base(k) for k in sd if _gate_base(k) != k}
+        self._tie()
+        self.keys = [k for k in network.trainable_keys(sd, pos) if k not in self.tied]
         self.m = {k: torch.zeros_like(sd[k]) for k in self.keys}
         self.v = {k: torch.zeros_like(sd[k]) for k in self.keys}
         self.num_heads, self.lr, self.gamma, self.clip = num_heads, lr, gamma, grad_norm_clip
         self.tuf, self.history = target_update_frequency, history
         self.num_train_steps = 0
 
+    def _tie(self):
+        for k, base in self.tied.items():
+            self.policy[k] = self.policy[base]
+
     def train_on_batch(self, batch):
         for k in self.keys:
             self.policy[k].requires_grad_(True)
-        loss, q, y = td_loss(self.policy, self.target, batch, self.num_heads, self.gamma, self.history)
+        loss, q, y = td_loss(self.policy, self.target, batch, self.num_heads, self.gamma, self.history, self.identity)
         grads = torch.autograd.grad(loss, [self.policy[k] for k in self.keys])
         for k in self.keys:
             self.policy[k].requires_grad_(False)
@@ -77,6 +92,7 @@ class TrainerOracle:
                 g = g * coef
                 self.policy[k], self.m[k], self.v[k] = adam_step(self.policy[k], g, self.m[k], self.v[k],
                                                                  self.num_train_steps, self.lr)
+        self._tie()
         if self.num_train_steps % self.tuf == 0:                        # dtqn.py:268-269
             self.target = {k: v.clone() for k, v in self.policy.items()}
         stats = dict(loss=loss.item(), grad_norm=total.item(), q_max=q.max().item(), q_mean=q.mean().item(),

@@ -48,7 +48,8 @@ def test_product_never_imports_oracle():
 
 class _NetCfg(ctypes.Structure):      # dtqn_net_cfg (include/dtqn_b200.h)
     _fields_ = [(n, ctypes.c_int32) for n in ("obs_dim", "num_actions", "d_model", "n_heads", "n_layers", "context_len",
-                                              "discrete", "vocab", "embed_per_obs", "pos_trainable")]
+                                              "discrete", "vocab", "embed_per_obs", "pos_trainable", "action_dim", "identity",
+                                              "gate_gru")] + [("dropout", ctypes.c_float), ("dropout_state", ctypes.c_void_p)]
 
 
 def test_layout_queries_run_on_the_host():
@@ -80,6 +81,14 @@ def test_layout_queries_run_on_the_host():
     bad = _NetCfg(O, A, 96, 8, layers, ctx, 0, 0, 0, 1)
     assert lib.dtqn_net_param_count(ctypes.byref(bad)) < 0
     assert lib.dtqn_net_workspace_floats(ctypes.byref(cfg), 0, 0) < 0
+    # ablation flags (run.py:98-103,151-167): --a-embed 8 swaps 8 observation-embedding columns for an [A, 8] action table,
+    # --gate gru adds ONE attention gate + ONE mlp gate (6 d^2 + d each) whatever the layer count, any d_model % 4 == 0 goes
+    n_a = lib.dtqn_net_param_count(ctypes.byref(_NetCfg(O, A, d, 8, layers, ctx, 0, 0, 0, 1, 8)))
+    assert n_a - n == A * 8 - 8 * O - 8
+    n_g = lib.dtqn_net_param_count(ctypes.byref(_NetCfg(O, A, d, 8, layers, ctx, 0, 0, 0, 1, 0, 0, 1)))
+    assert n_g - n == 2 * (6 * d * d + d)
+    assert lib.dtqn_net_param_count(ctypes.byref(_NetCfg(O, A, 96, 8, layers, ctx, 0, 0, 0, 1, 0, 1))) > 0
+    assert lib.dtqn_net_param_count(ctypes.byref(_NetCfg(O, A, d, 8, layers, ctx, 0, 0, 0, 1, 0, 0, 0, 0.5))) < 0   # dropout needs its state
     ws_act = lib.dtqn_net_workspace_floats(ctypes.byref(cfg), 4096 * ctx, 0)
     ws_train = lib.dtqn_net_workspace_floats(ctypes.byref(cfg), 3 * 32 * ctx, 1)
     assert ws_act > 4096 * ctx * d and ws_train > 3 * 32 * ctx * d * 2 * 10
