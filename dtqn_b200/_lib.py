@@ -28,7 +28,7 @@ class EnvStruct(C.Structure):
 
 class ReplayStruct(C.Structure):
     _fields_ = [("n_slots", C.c_int32), ("max_episode_steps", C.c_int32), ("obs_dim", C.c_int32),
-                ("context_len", C.c_int32), ("obs_mask", C.c_float), ("_pad", C.c_int32),
+                ("context_len", C.c_int32), ("obs_mask", C.c_float), ("record_every", C.c_int32),
                 ("obss", _p), ("actions", _p), ("rewards", _p), ("dones", _p), ("episode_lengths", _p),
                 ("slot_open", _p), ("counters", _p), ("env_slot", _p), ("env_prev_len", _p)]
 

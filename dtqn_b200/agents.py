@@ -71,7 +71,8 @@ class DtqnAgent:
                  max_env_steps: int, obs_mask: Union[int, float], num_actions: int, is_discrete_env: bool,
                  learning_rate: float = 0.0003, batch_size: int = 32, context_len: int = 50, gamma: float = 0.99,
                  grad_norm_clip: float = 1.0, target_update_frequency: int = 10_000, history: int = 50,
-                 bag_size: int = 0, n_envs: int = 1, trunc_context_obs: bool = True, sample_seed: int = 0, **kwargs):
+                 bag_size: int = 0, n_envs: int = 1, trunc_context_obs: bool = True, sample_seed: int = 0,
+                 record_every: int = 1, **kwargs):
         if bag_size:
             raise NotImplementedError("DTQN-bag is outside the hot path (SURVEY.md section 2 #23)")
         self.device = _lib.require_cuda(device)
@@ -89,7 +90,7 @@ class DtqnAgent:
         self.learning_rate, self.betas, self.adam_eps = float(learning_rate), (0.9, 0.999), 1e-8   # dqn.py:64
         self.replay_buffer = ReplayBuffer(buffer_size, env_obs_length=env_obs_length, obs_mask=obs_mask,
                                           max_episode_steps=max_env_steps, context_len=context_len, n_envs=n_envs,
-                                          device=self.device, sample_seed=sample_seed)
+                                          device=self.device, sample_seed=sample_seed, record_every=record_every)
         self.batch_size, self.gamma, self.grad_norm_clip = int(batch_size), float(gamma), float(grad_norm_clip)
         self.target_update_frequency = int(target_update_frequency)
         self.history = int(history)

@@ -15,7 +15,7 @@ from dtqn_b200 import _lib
 
 class ReplayBuffer:
     def __init__(self, buffer_size: int, env_obs_length: int, obs_mask: float, max_episode_steps: int,
-                 context_len: Optional[int] = 1, n_envs: int = 1, device=None, sample_seed: int = 0):
+                 context_len: Optional[int] = 1, n_envs: int = 1, device=None, sample_seed: int = 0, record_every: int = 1):
         dev = _lib.require_cuda(device)
         if isinstance(env_obs_length, tuple):
             raise NotImplementedError("image observations are outside the hot path (SURVEY.md section 2 #9)")
@@ -40,10 +40,12 @@ class ReplayBuffer:
         self.env_prev_len = torch.zeros((n_envs,), dtype=torch.int32, device=dev)
         self.draw_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.sample_seed = int(sample_seed)
+        self.record_every = int(record_every)       # K > 1: each env stores every K-th of its episodes (longer replay horizon)
         self._host_pos = [0, 0]            # used only by the single-env host-call API (store / flush)
         self._completed_seen = 0
         self.struct = _lib.ReplayStruct(
-            n_slots=S, max_episode_steps=E, obs_dim=O, context_len=self.context_len, obs_mask=self.obs_mask, _pad=0,
+            n_slots=S, max_episode_steps=E, obs_dim=O, context_len=self.context_len, obs_mask=self.obs_mask,
+            record_every=int(record_every),
             obss=_lib.ptr(self.obss), actions=_lib.ptr(self.actions), rewards=_lib.ptr(self.rewards),
             dones=_lib.ptr(self.dones), episode_lengths=_lib.ptr(self.episode_lengths),
             slot_open=_lib.ptr(self.slot_open), counters=_lib.ptr(self.counters),

@@ -250,7 +250,11 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
             atomicAdd((unsigned long long*)&e.ep_stats[3], 1ull);
         }
         if (frozen) done = 0;                                          // nothing to roll
-        e.done_flag[i] = (uint8_t)done;
+        // which of this env's episodes enter the replay: every record_every-th (episode index = episodes it has finished)
+        int flag = done;
+        if (done && has_rb && rb.record_every > 1 && e.env_acc && (e.env_acc[4 * (size_t)i] % rb.record_every) != 0) flag = 2;
+        e.done_flag[i] = (uint8_t)flag;
+        done = flag == 1;                                              // counted below: episodes that need a replay slot
     }
     const int cnt = __syncthreads_count(done);
     if (threadIdx.x == 0) e.block_counts[blockIdx.x] = cnt;
@@ -282,10 +286,11 @@ env_roll_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, int has_rb, int has
         for (int w = 0; w < ENV_THREADS / 32; ++w) { p += s_red[w]; t += s_tot[w]; }
         s_prefix = p; s_total = t;
     }
-    const int done = (i < e.n_envs) ? (int)e.done_flag[i] : 0;
+    const int flag = (i < e.n_envs) ? (int)e.done_flag[i] : 0;
+    const int done = flag == 1;                                        // finished AND its successor takes a replay slot
     const unsigned bal = __ballot_sync(0xffffffffu, done);
-    __syncthreads();
-    if (s_total == 0) return;                                          // nothing finished anywhere this step
+    const int any_roll = __syncthreads_or(flag != 0);
+    if (s_total == 0 && !any_roll) return;                             // nothing finished in this CTA / anywhere
     if (lane == 0) s_warp_off[warp] = __popc(bal);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -297,13 +302,14 @@ env_roll_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, int has_rb, int has
         rb.counters[1] = rb.counters[0] + s_total;                     // episodes started (published by the next step)
         rb.counters[2] += s_total;                                     // episodes completed
     }
-    if (!done) return;
+    if (!flag) return;
     const int rank = s_prefix + s_warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
     Pcg64 g; g.load(e.rng, e.rng_buf, e.n_envs, i);
     float o[O];
     env_reset_one<KIND>(e, i, g, o);                                   // run.py:295-296 env.reset()
     g.store(e.rng, e.rng_buf, e.n_envs, i);
-    if (has_rb) {                                                      // ReplayBuffer.store_obs at pos[0] % max_size
+    if (has_rb && !done) rb.env_slot[i] = -1;                          // this episode is not stored (record_every)
+    if (has_rb && done) {                                              // ReplayBuffer.store_obs at pos[0] % max_size
         const long long k = rb.counters[0] + rank;
         int s = (int)(k % rb.n_slots);
         if (rb.slot_open[s]) {                                         // ring wrapped onto a still-running episode

@@ -80,6 +80,7 @@ struct LayerAct {
     float *qkv, *o, *r1, *st1, *x1, *h, *r2, *st2, *x2;
 };
 struct NetAct {
+    float* lut;    // discrete observations: [groups][O][vocab][d] lookup table of the token embedding (embed_lut_kernel)
     float* x0;
     LayerAct layer[DTQN_MAX_LAYERS];
     float* hh;
@@ -91,6 +92,7 @@ static inline long long net_act_layout(const dtqn_net_cfg& c, long long T, int s
     const long long d = c.d_model;
     long long o = 0;
     auto take = [&](long long n) { float* p = base ? base + o : nullptr; o = al4(o + n); return p; };
+    A.lut = c.discrete ? take((long long)DTQN_MAX_GROUPS * c.obs_dim * c.vocab * d) : nullptr;
     A.x0 = take(T * d);
     for (int i = 0; i < c.n_layers; ++i) {
         if (i == 0 || save) {

@@ -28,6 +28,19 @@ __device__ __forceinline__ bool last_chunk_arrived(unsigned* ticket, unsigned n_
     return last;
 }
 
+// sum_{b < n} p[b * stride] in index order; the loads of a batch of 8 are independent (in flight together), the adds ordered
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, size_t stride, unsigned n) {
+    float sum = 0.f;
+    for (unsigned b0 = 0; b0 < n; b0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (b0 + k < n) ? __ldcg(p + (size_t)(b0 + k) * stride) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[k];
+    }
+    return sum;
+}
+
 // ---- TD loss: emits dLoss/dQ directly + the logged statistics (agents/dtqn.py:245-253) --------------------------------
 // q_all [3, B, L, A]: 0 = policy(obs), 1 = policy(next_obs), 2 = target(next_obs).
 __global__ void __launch_bounds__(256)
@@ -129,8 +142,7 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, cons
     }
     if (!last_chunk_arrived(ticket, gridDim.x)) return;
     for (int e = threadIdx.x; e < A * d + A; e += blockDim.x) {
-        float s = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (size_t)b * (A * d + A) + e);
+        const float s = ordered_sum(part + e, (size_t)(A * d + A), gridDim.x);
         if (e < A * d) gW2[e] = s; else gb2[e - A * d] = s;
     }
 }
@@ -169,16 +181,15 @@ dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const fl
 
 // ---- wgrad:  gW[Nf, Kf] = dY[T, Nf]^T X[T, Kf];  gb[Nf] = colsum(dY) ----------------------------------------------------------
 // 64 x 64 tile of gW per CTA, tokens split over gridDim.z chunks (split-K); chunk partials go to pW / pb (same indexing as
-// gW / gb, `pstride` floats between chunks) and the last CTA of a tile adds them in chunk order.
+// gW / gb, `pstride` floats between chunks); wgrad_reduce_kernel adds them in chunk order at the end of the backward pass.
 #define WG_CHUNK 64
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int Nf, int Kf,
-             float* __restrict__ gW, float* __restrict__ gb, float* __restrict__ pW, float* __restrict__ pb,
-             long long pstride, unsigned* __restrict__ tickets) {
+             float* __restrict__ gb, float* __restrict__ pW, float* __restrict__ pb, long long pstride, int chunk) {
     __shared__ __align__(16) float As[16][64 + 4];   // dY slab: 16 tokens x 64 n   (float4 accesses: keep 16-byte aligned
     __shared__ __align__(16) float Bs[16][64 + 4];   // X  slab: 16 tokens x 64 k    whatever else lives in static shared memory)
     const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
-    const int tb = blockIdx.z * WG_CHUNK, te = min(T, tb + WG_CHUNK);
+    const int tb = blockIdx.z * chunk, te = min(T, tb + chunk);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int lr = tid >> 4, lc = (tid & 15) * 4;            // slab load: row lr (token), 4 columns at lc
     float acc[4][4];
@@ -215,24 +226,31 @@ wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, i
     for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(pW + poff + (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4) =
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    const bool do_bias = gb && blockIdx.y == 0;
-    if (do_bias && tid < 64) pb[poff + n0 + tid] = bsum;
-    if (!last_chunk_arrived(tickets + blockIdx.y * gridDim.x + blockIdx.x, gridDim.z)) return;
+    if (gb && blockIdx.y == 0 && tid < 64) pb[poff + n0 + tid] = bsum;
+}
+
+// Chunk-ordered sum of the split-K partials of every Linear weight / bias: grads[e] = sum_z partial[z][e] for e in the
+// contiguous [in_w .. f2_b] block of each layer and the [h1_w .. h1_b] block of the head (same offsets in the partial rows as
+// in the flat gradient).  One launch for the whole network, one float4 per thread, the loads of 4 chunks in flight together.
+struct WgradSegs { long long begin[DTQN_MAX_LAYERS + 1], len4[DTQN_MAX_LAYERS + 1]; int n; long long total4; };
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, long long pstride, int n_chunks, WgradSegs segs, float* __restrict__ grads) {
+    long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (q >= segs.total4) return;
+    int sgi = 0;
+    while (q >= segs.len4[sgi]) { q -= segs.len4[sgi]; ++sgi; }
+    const long long e = segs.begin[sgi] + 4 * q;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z0 = 0; z0 < n_chunks; z0 += 4) {
+        float4 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const size_t o = (size_t)(n0 + ty * 4 + i) * Kf + k0 + tx * 4;
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (unsigned z = 0; z < gridDim.z; ++z) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(pW + (size_t)z * pstride + o));
-            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-        }
-        *reinterpret_cast<float4*>(gW + o) = sum;
+        for (int zz = 0; zz < 4; ++zz)
+            v[zz] = (z0 + zz < n_chunks) ? __ldcg(reinterpret_cast<const float4*>(partial + (size_t)(z0 + zz) * pstride + e))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int zz = 0; zz < 4; ++zz) { sum.x += v[zz].x; sum.y += v[zz].y; sum.z += v[zz].z; sum.w += v[zz].w; }
     }
-    if (do_bias && tid < 64) {
-        float sum = 0.f;
-        for (unsigned z = 0; z < gridDim.z; ++z) sum += __ldcg(pb + (size_t)z * pstride + n0 + tid);
-        gb[n0 + tid] = sum;
-    }
+    *reinterpret_cast<float4*>(grads + e) = sum;
 }
 
 // ---- LayerNorm backward fused with the ReLU / residual split (transformer.py:72-73,76-77) -----------------------------------
@@ -284,8 +302,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xin, const
     }
     if (!last_chunk_arrived(ticket, gridDim.x)) return;
     for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-        float sum = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * 2 * D + c);
+        const float sum = ordered_sum(part + c, (size_t)(2 * D), gridDim.x);
         if (c < D) ggamma[c] = sum; else gbeta[c - D] = sum;
     }
 }
@@ -455,14 +472,19 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
             mypart[d * KI + d + e] = s;
         }
     }
-    if (!last_chunk_arrived(ticket, gridDim.x)) return;
-    for (int e = threadIdx.x; e < n_part; e += blockDim.x) {
-        float sum = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(part + (size_t)b * n_part + e);
-        if (e < d * KI) g_w[e] = sum;
-        else if (e < d * KI + d) g_b[e - d * KI] = sum;
-        else g_table[e - d * KI - d] = sum;
-    }
+    (void)ticket;                                             // the per-CTA partials are summed by embed_reduce_kernel
+}
+// CTA-ordered sum of the embedding-gradient partials: one thread per gradient element (the discrete embedding has ~10 k of
+// them: a single last CTA walking 50 partial rows of each would serialise ~200 us)
+__global__ void __launch_bounds__(256)
+embed_reduce_kernel(const float* __restrict__ part, int n_blocks, int n_part, int n_w, int n_b, float* __restrict__ g_w,
+                    float* __restrict__ g_b, float* __restrict__ g_table) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_part) return;
+    const float sum = ordered_sum(part + e, (size_t)n_part, (unsigned)n_blocks);
+    if (e < n_w) g_w[e] = sum;
+    else if (e < n_w + n_b) g_b[e - n_w] = sum;
+    else g_table[e - n_w - n_b] = sum;
 }
 
 
@@ -493,6 +515,7 @@ struct SideStream {
 };
 SideStream g_side;
 int g_parallel_wgrad = 1;
+int g_wgrad_chunk = 2 * WG_CHUNK;  // tokens per split-K chunk of the weight-gradient GEMMs (multiple of 16, >= WG_CHUNK); 128 measured best
 
 template <int EPI>
 int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
@@ -507,12 +530,12 @@ int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, i
 }
 
 // pW / pb: chunk-partial areas of this weight / bias (same offsets as in the flat gradient), pstride floats between chunks
-int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gW, float* gb, float* pW, float* pb,
-                 long long pstride, unsigned* tickets, cudaStream_t st) {
-    if (Nf % 64 || Kf % 64 || (Nf / 64) * (Kf / 64) > 64) return DTQN_E_UNSUPPORTED;
-    dim3 grid(Nf / 64, Kf / 64, dtqn_cdiv(T, WG_CHUNK));
+int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* gb, float* pW, float* pb,
+                 long long pstride, cudaStream_t st) {
+    if (Nf % 64 || Kf % 64) return DTQN_E_UNSUPPORTED;
+    dim3 grid(Nf / 64, Kf / 64, dtqn_cdiv(T, g_wgrad_chunk));
     prof_begin(PROF_WGRAD, st);
-    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gW, gb, pW, pb, pstride, tickets);
+    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, T, Nf, Kf, gb, pW, pb, pstride, g_wgrad_chunk);
     prof_end(PROF_WGRAD, st, 2.0 * (double)T * Nf * Kf);
     DTQN_LAUNCH_CHECK();
     return 0;
@@ -548,6 +571,11 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
 }  // namespace
 
 extern "C" int dtqn_set_parallel_wgrad(int32_t on) { g_parallel_wgrad = on; return 0; }
+extern "C" int dtqn_set_wgrad_chunk(int32_t tokens) {
+    if (tokens < WG_CHUNK || tokens % 16) return DTQN_E_ARG;      // the partial buffer is sized for WG_CHUNK-token chunks
+    g_wgrad_chunk = tokens;
+    return 0;
+}
 
 extern "C" int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t seq_len) {
     if (!cfg || batch < 1 || seq_len < 1) return DTQN_E_ARG;
@@ -609,8 +637,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     auto fork = [&]() { if (par) g_side.fork(st); };
     // weight gradient of the Linear whose weight / bias sit at w_off / b_off of the flat layout (split-K, fixed-order sum)
     auto wgrad = [&](const float* dY, const float* X, int Nf, int Kf, long long w_off, long long b_off) {
-        return launch_wgrad(dY, X, Ti, Nf, Kf, grads + w_off, grads + b_off, s.pgrad + w_off, s.pgrad + b_off, lay.total,
-                            s.ticket + 8, ws_);
+        return launch_wgrad(dY, X, Ti, Nf, Kf, grads + b_off, s.pgrad + w_off, s.pgrad + b_off, lay.total, ws_);
     };
     const float* x_last = act.layer[cfg->n_layers - 1].x2;
     fork();
@@ -663,6 +690,21 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
         if (par) g_side.join(st);          // the next layer overwrites ga / gh / gqkv / ga1
     }
+    // every weight-gradient GEMM has been joined: chunk-ordered sum of their partials into the flat gradient
+    {
+        WgradSegs segs{};
+        long long tot = 0;
+        for (int li = 0; li <= cfg->n_layers; ++li) {
+            const long long b = li < cfg->n_layers ? lay.layer[li].in_w : lay.h1_w;
+            const long long e = li < cfg->n_layers ? lay.layer[li].f2_b + d : lay.h1_b + d;
+            segs.begin[li] = b; segs.len4[li] = (e - b) / 4; tot += (e - b) / 4;
+        }
+        segs.n = cfg->n_layers + 1; segs.total4 = tot;
+        prof_begin(PROF_WGRAD, st);
+        wgrad_reduce_kernel<<<dtqn_cdiv(tot, 256), 256, 0, st>>>(s.pgrad, lay.total, dtqn_cdiv(Ti, g_wgrad_chunk), segs, grads);
+        prof_end(PROF_WGRAD, st, 0.0);
+        DTQN_LAUNCH_CHECK();
+    }
     // embedding + position table
     prof_begin(PROF_OTHER, st);
     if (cfg->pos_trainable) {
@@ -675,6 +717,10 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         embed_bwd_kernel<<<dtqn_cdiv(T0, 32), 256, smem, st>>>(s.gx, *obs_src, *cfg, params, lay.emb_table, lay.emb_w, L, Ti,
                                                               cfg->discrete ? grads + lay.emb_table : nullptr,
                                                               grads + lay.emb_w, grads + lay.emb_b, s.psmall, s.ticket + 3);
+        DTQN_LAUNCH_CHECK();
+        const int n_part = d * KI + d + (cfg->discrete ? cfg->vocab * cfg->embed_per_obs : 0);
+        embed_reduce_kernel<<<dtqn_cdiv(n_part, 256), 256, 0, st>>>(s.psmall, dtqn_cdiv(T0, 32), n_part, d * KI, d, grads + lay.emb_w,
+                                                                    grads + lay.emb_b, cfg->discrete ? grads + lay.emb_table : nullptr);
         DTQN_LAUNCH_CHECK();
     }
     prof_end(PROF_OTHER, st, 0.0);

@@ -122,6 +122,65 @@ embed_cont_kernel(GroupPtrs P, GroupSrc S, int O, long long emb_w, long long emb
     }
 }
 
+// Discrete observations, table-lookup form.  Embedding -> Flatten -> Linear is linear in the one-hot of every feature, so
+//   x[c] = b[c] + sum_k LUT[k][tok_k][c],   LUT[k][v][c] = sum_e table[v][e] * W[c][k*E + e]
+// (representations.py:47-51 regrouped: the e-sum of a feature first, then the features in order).  embed_lut_build_kernel
+// writes the O x vocab x D table of every group's network once per forward (vocab is 9 for Memory-5: 46 KB at D = 128, 92 k
+// MACs); embed_lut_kernel stages it in shared memory and streams tokens: one warp per token (pair), a lane adds O float4 rows
+// of the table + the position row and writes 16 bytes -- O adds per channel instead of O*E multiply-adds, bound by the write
+// of x0 (HBM) instead of the fp32 pipe.
+__global__ void __launch_bounds__(256)
+embed_lut_build_kernel(GroupPtrs P, int O, int E, int vocab, int D, long long emb_table, long long emb_w, float* __restrict__ lut) {
+    const int g = blockIdx.y, n = O * vocab * D, KI = O * E;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    const float* p = P.p[g];
+    const int c = e % D, v = (e / D) % vocab, k = e / (D * vocab);
+    float a = 0.f;
+    for (int q = 0; q < E; ++q) a = fmaf(__ldg(p + emb_table + v * E + q), __ldg(p + emb_w + (long long)c * KI + k * E + q), a);
+    lut[(size_t)g * n + e] = a;
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+embed_lut_kernel(GroupPtrs P, GroupSrc S, int O, int vocab, const float* __restrict__ lut, long long emb_b,
+                 long long pos_off, int n_seq, int L, float obs_mask, float* __restrict__ x0) {
+    extern __shared__ __align__(16) float el_sm[];
+    float* sLut = el_sm;                                       // [O][vocab][D]
+    float* sB = sLut + (size_t)O * vocab * D;                  // [D]
+    const int g = blockIdx.z, tid = threadIdx.x, n_lut = O * vocab * D;
+    const float* p = P.p[g];
+    for (int e = tid * 4; e < n_lut; e += 1024)
+        *reinterpret_cast<float4*>(sLut + e) = __ldg(reinterpret_cast<const float4*>(lut + (size_t)g * n_lut + e));
+    for (int e = tid; e < D; e += 256) sB[e] = __ldg(p + emb_b + e);
+    __syncthreads();
+    constexpr int LPT = D / 4;                                 // lanes per token (16 or 32), one float4 of channels each
+    constexpr int TPW = 32 / LPT;                              // tokens per warp pass
+    const int lane = tid & 31, warp = tid >> 5;
+    const int c4 = (lane % LPT) * 4, sub = lane / LPT;
+    const dtqn_obs_src s = S.s[g];
+    const long long Tg = (long long)n_seq * L;
+    for (long long t = ((long long)blockIdx.x * 8 + warp) * TPW + sub; t < Tg; t += (long long)gridDim.x * 8 * TPW) {
+        const int i = (int)(t / L), j = (int)(t % L);
+        int row = j; bool valid = true;
+        if (s.timestep) {
+            const int ts = __ldg(s.timestep + i);
+            const int n = min(s.ring_len, ts + 1);
+            valid = j < n;
+            row = valid ? (ts + 1 - n + j) % s.ring_len : 0;
+        }
+        const float* ob = s.obs + (long long)i * s.seq_stride + (long long)row * O;
+        float4 acc = *reinterpret_cast<const float4*>(sB + c4);
+        for (int k = 0; k < O; ++k) {
+            int tok = (int)(valid ? __ldg(ob + k) : obs_mask);
+            tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+            const float4 r = *reinterpret_cast<const float4*>(sLut + ((size_t)k * vocab + tok) * D + c4);
+            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+        }
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(p + pos_off + (long long)j * D + c4));
+        *reinterpret_cast<float4*>(x0 + ((long long)g * Tg + t) * D + c4) = make_float4(acc.x + pv.x, acc.y + pv.y, acc.z + pv.z, acc.w + pv.w);
+    }
+}
+
 // Discrete observations (Embedding(vocab, E) per feature -> Flatten -> Linear(O*E, D), representations.py:47-51), fast path:
 // ED_TOK tokens per CTA.  The Linear weight is staged TRANSPOSED in shared memory once per CTA ([KI][D + 4]: float4 reads
 // along the channels are conflict-free), every token's flattened embedding row is gathered from the (staged) table, and each
@@ -742,7 +801,28 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
         if (!cfg->discrete && cfg->obs_dim <= 16) {
             if (d == 64) embed_cont_kernel<64><<<dim3(dtqn_cdiv(Tg, 64), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, src[0].obs_mask, act.x0);
             else         embed_cont_kernel<128><<<dim3(dtqn_cdiv(Tg, 32), 1, G), 256, 0, st>>>(P, S, cfg->obs_dim, lay.emb_w, lay.emb_b, lay.pos, n_seq, L, src[0].obs_mask, act.x0);
-        } else if (cfg->discrete && g_embed_disc_fast && lay.k_in <= 128) {
+        } else if (cfg->discrete && g_embed_disc_fast == 1 && (d == 64 || d == 128) &&
+                   sizeof(float) * ((size_t)cfg->obs_dim * cfg->vocab * d + d) <= 96 * 1024) {
+            const size_t smem = sizeof(float) * ((size_t)cfg->obs_dim * cfg->vocab * d + d);
+            const int n_lut = cfg->obs_dim * cfg->vocab * d;
+            embed_lut_build_kernel<<<dim3(dtqn_cdiv(n_lut, 256), G), 256, 0, st>>>(P, cfg->obs_dim, cfg->embed_per_obs, cfg->vocab, d,
+                                                                                  lay.emb_table, lay.emb_w, act.lut);
+            DTQN_LAUNCH_CHECK();
+            long long passes = dtqn_cdiv(Tg, 8 * (128 / d));
+            dim3 grid((unsigned)(passes < 2 * 148 ? passes : 2 * 148), 1, G);   // persistent: the table is staged once per CTA
+            const float mask = (float)(cfg->vocab - 1);
+            cudaError_t ae;
+            if (d == 64) {
+                ae = cudaFuncSetAttribute(embed_lut_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ae == cudaSuccess)
+                    embed_lut_kernel<64><<<grid, 256, smem, st>>>(P, S, cfg->obs_dim, cfg->vocab, act.lut, lay.emb_b, lay.pos, n_seq, L, mask, act.x0);
+            } else {
+                ae = cudaFuncSetAttribute(embed_lut_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ae == cudaSuccess)
+                    embed_lut_kernel<128><<<grid, 256, smem, st>>>(P, S, cfg->obs_dim, cfg->vocab, act.lut, lay.emb_b, lay.pos, n_seq, L, mask, act.x0);
+            }
+            if (ae != cudaSuccess) return (int)ae;
+        } else if (cfg->discrete && g_embed_disc_fast == 2 && lay.k_in <= 128) {   // previous form (kept for A/B timing: dtqn_set_embed_disc_fast(2))
             const int KI = lay.k_in;
             const size_t smem = sizeof(float) * ((size_t)KI * (d + 4) + d + ((cfg->vocab * cfg->embed_per_obs + 3) & ~3) + (size_t)ED_TOK * KI);
             long long chunks = dtqn_cdiv(Tg, ED_TOK);

@@ -182,7 +182,9 @@ var_embed_kernel(GroupPtrs P, GroupSrc S, dtqn_net_cfg c, NetLayout lay, int n_s
     float v;
     if (col < ad) {
         v = 0.f;
-        const int ja = L > 1 ? j - 1 : j;
+        // the reference forwards only the n valid tokens of an acting context, so its `history_len > 1` test sees n, not L
+        const int n_tok = s.timestep ? min(min(s.ring_len, s.timestep[i] + 1), L) : L;
+        const int ja = n_tok > 1 ? j - 1 : j;
         if (ja >= 0) {
             bool valid; const int row = var_ring_row(s, i, ja, valid);
             const int a = valid ? (int)s.actions[(long long)i * s.act_stride + row] : 0;

@@ -20,7 +20,7 @@ class BatchedTrainer:
                  buf_size: Optional[int] = None, lr: float = 3e-4, tuf: int = 10_000, gamma: float = 0.99,
                  history: Optional[int] = None, num_steps: int = 2_000_000, obs_embed: int = 8,
                  trunc_context_obs: bool = True, pos: str = "learned", max_episode_steps: Optional[int] = None,
-                 a_embed: int = 0, dropout: float = 0.0, identity: bool = False, gate: str = "res"):
+                 a_embed: int = 0, dropout: float = 0.0, identity: bool = False, gate: str = "res", record_every: int = 1):
         rank, world = rank_world()
         self.rank, self.world = rank, world
         self.device = _lib.require_cuda(device)
@@ -34,7 +34,7 @@ class BatchedTrainer:
         self.agent = get_agent("DTQN", [self.env], obs_embed, a_embed, inner_embed, buf_size, self.device, lr, batch, context,
                                E, history or context, tuf, gamma, num_heads=heads, num_layers=layers, dropout=dropout,
                                identity=identity, gate=gate, pos=pos, n_envs=n_envs,
-                               trunc_context_obs=trunc_context_obs, sample_seed=seed * 7919 + rank)
+                               trunc_context_obs=trunc_context_obs, sample_seed=seed * 7919 + rank, record_every=record_every)
         if world > 1:
             broadcast_parameters(self.agent.policy_network.flat, src=0)
             self.agent.policy_network.packed_stale = True

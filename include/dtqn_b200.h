@@ -60,7 +60,8 @@ typedef struct dtqn_env {
     uint64_t* shown;            /* [n] Memory observation, 4 bits per card (0 hidden, 1..5 shown, 6 removed) */
     int32_t*  cur;              /* [n] Memory currently shown card */
     int32_t*  elapsed;          /* [n] TimeLimit._elapsed_steps */
-    uint8_t*  done_flag;        /* [n] scratch: episode ended in this step (consumed by the roll kernel) */
+    uint8_t*  done_flag;        /* [n] scratch: episode ended in this step (1: its successor is stored in the replay, 2: it is
+                                   not -- see dtqn_replay.record_every); consumed by the roll kernel */
     int32_t*  block_counts;     /* [ceil(n/256)] scratch: episodes finished per CTA in this step */
     int64_t*  ep_stats;         /* [4] running sums over finished episodes: return, length, successes, episodes */
     int32_t*  ep_return;        /* [n] return of the running episode (rewards are integers in both envs) */
@@ -77,7 +78,11 @@ typedef struct dtqn_replay {
     int32_t obs_dim;
     int32_t context_len;
     float   obs_mask;           /* -5 (Box) | 8 (MultiDiscrete), utils/env_processing.py:100-118 */
-    int32_t _pad;
+    int32_t record_every;       /* <= 1: every episode is stored (the reference); K > 1: each env stores every K-th of its
+                                   episodes, so a ring of S slots spans K times more loop iterations (with thousands of
+                                   lockstep envs per update almost all transitions are never sampled anyway; what the
+                                   reference's 500 000-transition buffer provides is a memory of ~25 % of the RUN, i.e. of
+                                   many target-network periods, and this keeps that horizon at scale) */
     float*   obss;              /* [S, E+1, O] */
     uint8_t* actions;           /* [S, E+1]    */
     float*   rewards;           /* [S, E]      */
@@ -241,8 +246,10 @@ int dtqn_set_attn_mma(int32_t on);
  * and the attention row of the last valid position as ONE persistent tcgen05 kernel per 128-token tile (no activations
  * in HBM); 0: one kernel per GEMM / attention. */
 int dtqn_set_act_fused(int32_t on);
-/* 1 (default): discrete observations (Embedding -> Flatten -> Linear, representations.py:47-51) use the kernel that stages
- * the transposed Linear weight and the table in shared memory; 0: the generic per-channel kernel (same arithmetic). */
+/* Discrete observations (Embedding -> Flatten -> Linear, representations.py:47-51).  1 (default): table-lookup form -- every CTA
+ * builds LUT[feature][value][channel] = table[value] . W[channel, feature block] in shared memory and a token costs O row adds;
+ * 2: the kernel that stages the transposed Linear weight and the table in shared memory (reference summation order);
+ * 0: the generic per-channel kernel. */
 int dtqn_set_embed_disc_fast(int32_t on);
 /* debug: device buffer of >= 256 int64 that receives clock64 phase stamps of CTA 0 of the fused acting kernel (NULL: off). */
 int dtqn_set_act_fused_timeline(void* device_buf);
@@ -263,6 +270,9 @@ int64_t dtqn_td_scratch_floats(const dtqn_net_cfg* cfg, int32_t batch, int32_t s
 /* 1 (default): weight-gradient GEMMs run on a library-owned side stream, forked / joined with events around each layer
  * (graph edges under capture); 0: everything on the caller's stream. */
 int dtqn_set_parallel_wgrad(int32_t on);
+/* Tokens per split-K chunk of the weight-gradient GEMMs (default 128, multiple of 16, >= 64): each chunk's partial tile is
+ * stored and the last CTA of a tile adds the chunks in order (deterministic; no fp32 atomics). */
+int dtqn_set_wgrad_chunk(int32_t tokens);
 
 /* clip_grad_norm_(params, max_norm, error_if_nonfinite=True) + Adam.step (dtqn/agents/dtqn.py:257-265,
  * dtqn/agents/dqn.py:64): grads *= grad_scale (1/world after the allreduce), total = ||grads||_2,

@@ -93,7 +93,7 @@ def test_variant_train_step_vs_oracle(name, d, H, ctx, B):
                 assert err <= 1e-3 * max(float(gr.abs().max()), 1e-3 * gmax), (name, k, err, float(gr.abs().max()))
     for k, p in agent.policy_network.state_dict().items():
         if not k.endswith("attn_mask"):
-            assert float((p.cpu() - tr.policy[k]).abs().max()) < 2e-5, (name, k)
+            assert float((p.cpu() - tr.policy[k]).abs().max()) < 5e-5, (name, k)   # two Adam steps of 3e-4 each
 
 
 def test_action_embedding_acting_context_matches_oracle():
@@ -161,7 +161,7 @@ def test_dropout_masks_and_gradients():
     a = out.clone()
     lib.dtqn_dropout_scales(8, 3, p, out.numel(), out.data_ptr(), _lib.stream_ptr())
     assert 0.3 < float((a != out).float().mean()) < 0.45            # a new counter value draws fresh masks: 2 p (1 - p) differ
-    O, A, d, H, ctx, B = 3, 3, 32, 4, 8, 3
+    O, A, d, H, ctx, B = 3, 3, 64, 8, 8, 3          # d = 64 so that the p = 0 twin is a default-architecture network
     mk = lambda pp: DTQN(O, A, 8, 0, d, H, 2, ctx, dropout=pp, pos="learned", device="cuda")
     agent = DtqnAgent(lambda: mk(p), 4000, "cuda", O, 200, -5, A, False, batch_size=B, context_len=ctx, history=ctx)
     g = torch.Generator().manual_seed(1)
@@ -175,7 +175,8 @@ def test_dropout_masks_and_gradients():
     plain.load_state_dict(net.state_dict())
     x = torch.empty(5, ctx, O).uniform_(-1, 1, generator=g)
     net.eval()
-    assert torch.equal(net(x), plain(x))                           # eval mode: dropout is the identity
+    # eval mode: dropout is the identity (the p = 0 twin runs the fused default-architecture kernels: same values, other order)
+    assert float((net(x) - plain(x)).abs().max()) <= 1e-5 * float(plain(x).abs().max())
     net.train()
     q1, q2 = net(x), net(x)
     assert not torch.equal(q1, q2) and not torch.equal(q1, plain(x))
