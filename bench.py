@@ -516,11 +516,16 @@ def main():
                         "launches_timed": v["n"], "avg_us_per_launch": 1e3 * v["ms"] / v["n"]}
             if nm == "act_fused_tcgen05":
                 try:
-                    with open(os.path.join(ROOT, "profiles", "r1_act_fused_ncu.json")) as f:
+                    src = next(n for n in ("r2_act_fused_ncu.json", "r1_act_fused_ncu.json")
+                               if os.path.exists(os.path.join(ROOT, "profiles", n)))
+                    with open(os.path.join(ROOT, "profiles", src)) as f:
                         aj = json.load(f)
                     roof["traffic"] = aj["dram_bytes_read_per_launch"] + aj["dram_bytes_write_per_launch"]
-                    roof["traffic_note"] = ("dram__bytes_read + write of one launch (ncu --set full, profiles/r1_act_fused_ncu.json): the "
+                    roof["traffic_note"] = (f"dram__bytes_read + write of one launch (ncu --set full, profiles/{src}): the "
                                             "context rows and the weight image; every activation stays in shared memory / TMEM")
+                    roof["burst_peak_view"] = {"peak": pk["tf_burst"], "frac": ach / pk["tf_burst"],
+                                               "note": "against the burst bf16 peak (a kernel timed alone); the line's frac uses the sustained "
+                                                       "peak because the kernel is timed inside a long step"}
                     roof["tensor_view"] = {"sm__pipe_tensor_cycles_active_pct": aj["sm__pipe_tensor_cycles_active_pct"],
                                            "note": "achieved = ALGORITHMIC FLOPs (embed + layer 0 + final-layer in_proj + last-row attention) / "
                                                    "launch time; the bf16 hi/lo split issues 3 MMAs per algorithmic MMA, so this fraction is "

@@ -20,7 +20,8 @@ class BatchedTrainer:
                  buf_size: Optional[int] = None, lr: float = 3e-4, tuf: int = 10_000, gamma: float = 0.99,
                  history: Optional[int] = None, num_steps: int = 2_000_000, obs_embed: int = 8,
                  trunc_context_obs: bool = True, pos: str = "learned", max_episode_steps: Optional[int] = None,
-                 a_embed: int = 0, dropout: float = 0.0, identity: bool = False, gate: str = "res", record_every: int = 1):
+                 a_embed: int = 0, dropout: float = 0.0, identity: bool = False, gate: str = "res", record_every: int = 1,
+                 updates_per_step: int = 1):
         rank, world = rank_world()
         self.rank, self.world = rank, world
         self.device = _lib.require_cuda(device)
@@ -55,6 +56,10 @@ class BatchedTrainer:
         self.eps = LinearAnneal(1.0, 0.1, max(1, num_steps // 10))     # run.py:420
         self.env.reset_all()                                  # run.py:287-288
         self.n_envs = n_envs
+        # the reference does 1 update per env step of ONE env (run.py:297); with thousands of lockstep envs per update the
+        # data : update ratio is n_envs x larger -- K > 1 performs K sample / train rounds per lockstep step
+        self.updates_per_step = int(updates_per_step)
+        assert self.updates_per_step >= 1
         self.iterations = 0
         self._graph = None
         # exploration schedule mirrored on the device: a replayed graph reads / anneals it without any host write
@@ -71,11 +76,14 @@ class BatchedTrainer:
         agent, rb = self.agent, self.agent.replay_buffer
         self._device_epsilon()
         agent.act_and_step(self.env, 0.0, epsilon_dev=self._eps_dev)
-        eps, starts = rb.draw_indices(agent.batch_size)
-        rb.gather_windows(eps, starts, out=agent._win)
-        agent.forward_backward(*agent._win[:4])
-        if self._update_in_graph:
-            agent.reduce_and_step()
+        for k in range(self.updates_per_step):
+            eps, starts = rb.draw_indices(agent.batch_size)
+            rb.gather_windows(eps, starts, out=agent._win)
+            agent.forward_backward(*agent._win[:4])
+            if self._update_in_graph:
+                agent.reduce_and_step()
+            else:
+                assert self.updates_per_step == 1, "updates_per_step > 1 needs the update inside the graph (1 GPU or the fused NVLink exchange)"
 
     def _sync_epsilon_to_device(self) -> None:
         self._eps_state.copy_(torch.tensor([self.eps.val, getattr(self.eps, "min", self.eps.val),
@@ -104,7 +112,8 @@ class BatchedTrainer:
         self._graph = g
         if not self._update_in_graph:
             self.agent.reduce_and_step()
-        self.agent.finish_step()
+        for _ in range(self.updates_per_step):
+            self.agent.finish_step()
         self.eps.anneal()
         self.iterations += 1
 
@@ -143,10 +152,12 @@ class BatchedTrainer:
             self._graph.replay()
             if not self._update_in_graph:
                 self.agent.reduce_and_step()
-            self.agent.finish_step()
+            for _ in range(self.updates_per_step):
+                self.agent.finish_step()
         else:
             self.agent.act_and_step(self.env, self.eps.val)
-            self.agent.train()
+            for _ in range(self.updates_per_step):
+                self.agent.train()
         self.eps.anneal()
         self.iterations += 1
 

@@ -168,3 +168,37 @@ def test_evaluate_matches_oracle_greedy_rollouts(golden_dir):
                 succ += int(info.get("is_success", False) or ep_r > 0)
             mism += (int(acc[i, 1]), int(acc[i, 2]), int(acc[i, 3])) != (int(ret), int(length), int(succ))
     assert mism == 0, f"{mism} of {2 * N} per-env evaluation records differ from the oracle rollout"
+
+
+def test_updates_per_step_and_record_every():
+    """New scale knobs (no reference analogue: it has one env): K gradient updates per lockstep step, and every K-th episode
+    of each env stored in the replay.  Eager and graph replay stay bit-identical; the optimiser has taken K steps per
+    iteration; with record_every = 4 a quarter of the finished episodes took a replay slot and every closed slot is a whole,
+    valid episode."""
+    a, b = _trainer(updates_per_step=3, record_every=4), _trainer(updates_per_step=3, record_every=4)
+    for t in (a, b):
+        t.prepopulate(400)
+        assert t.agent.replay_buffer.can_sample(16)
+    b.enable_graphs()
+    a.train_iteration()
+    for _ in range(5):
+        a.train_iteration(); b.train_iteration()
+    torch.cuda.synchronize()
+    assert a.agent.num_train_steps == b.agent.num_train_steps == 18 and int(b.agent.opt_step.item()) == 18
+    assert torch.equal(a.agent.policy_network.flat, b.agent.policy_network.flat)
+    rb, env = a.agent.replay_buffer, a.env
+    c = rb.counters.cpu().numpy()
+    finished = int(env.ep_stats[3].item())
+    per_env = env.env_acc[:, 0].cpu().numpy()
+    recorded = int((per_env // 4 + 1).sum())                   # episodes 0, 4, 8, ... of each env (incl. the running one)
+    assert c[1] == recorded and c[3] == 0 and finished == per_env.sum()
+    used = min(int(c[1]), rb.max_size)
+    lens = rb.episode_lengths[:used].cpu().numpy()
+    open_ = rb.slot_open[:used].cpu().numpy().astype(bool)
+    obss = rb.obss[:used].cpu().numpy()
+    for s in np.where(~open_)[0][:300]:
+        L = lens[s]
+        assert 1 <= L <= 200 and np.all(obss[s, : L + 1, 0] != -5.0) and np.all(obss[s, L + 1:] == -5.0)
+        assert np.all(np.abs(np.diff(obss[s, : L + 1, 0])) <= 0.0700001)        # one trajectory: |dp| <= max velocity
+    slots = rb.env_slot.cpu().numpy()
+    assert ((slots >= 0) == (per_env % 4 == 0)).all()          # envs whose running episode is not stored hold slot -1

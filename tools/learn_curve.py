@@ -32,6 +32,7 @@ ap.add_argument("--prepopulate", type=int, default=50_000, help="random-policy t
 ap.add_argument("--trunc", type=int, default=1, help="1 = the reference's integer acting context (SURVEY A-Q2)")
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--record-every", type=int, default=1, help="each env stores every K-th episode (replay horizon x K)")
+ap.add_argument("--updates-per-step", type=int, default=1, help="gradient updates per lockstep env step")
 ap.add_argument("--budget-s", type=float, default=1e9, help="stop (cleanly) after this many seconds of wall-clock")
 ap.add_argument("--out", default="gpurun_out/learn_curve.jsonl")
 a = ap.parse_args()
@@ -39,14 +40,14 @@ a = ap.parse_args()
 E = 200 if "CarFlag" in a.env else 50
 tr = BatchedTrainer(a.env, n_envs=a.n_envs, seed=a.seed, buf_size=max(a.buf_size, 8 * a.n_envs * E), device="cuda",
                     inner_embed=a.in_embed, context=50, batch=a.batch, lr=a.lr, tuf=a.tuf, num_steps=a.num_steps or a.iters,
-                    trunc_context_obs=bool(a.trunc), record_every=a.record_every)
+                    trunc_context_obs=bool(a.trunc), record_every=a.record_every, updates_per_step=a.updates_per_step)
 tr.prepopulate(max(1, a.prepopulate // a.n_envs))
 while not tr.agent.replay_buffer.can_sample(a.batch):
     tr.prepopulate(64)
 tr.enable_graphs()
 os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
 k = max(1, -(-a.eval_episodes // a.n_envs))
-cfg = {k_: getattr(a, k_) for k_ in ("env", "n_envs", "iters", "batch", "tuf", "lr", "in_embed", "buf_size", "trunc", "seed", "record_every")}
+cfg = {k_: getattr(a, k_) for k_ in ("env", "n_envs", "iters", "batch", "tuf", "lr", "in_embed", "buf_size", "trunc", "seed", "record_every", "updates_per_step")}
 
 
 def log(it, wall):
