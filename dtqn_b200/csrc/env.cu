@@ -227,6 +227,7 @@ env_step_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, dtqn_step_io io, in
                         rb.dones[(size_t)s * E + tt] = 1;
                     }
                     rb.slot_open[s] = 0;
+                    atomicAdd((unsigned long long*)&rb.counters[2], 1ull);       // a stored episode completed (can_sample)
                 }
             }
         }
@@ -300,7 +301,6 @@ env_roll_kernel(dtqn_env e, dtqn_replay rb, dtqn_context cx, int has_rb, int has
     __syncthreads();
     if (has_rb && blockIdx.x == 0 && threadIdx.x == 0) {
         rb.counters[1] = rb.counters[0] + s_total;                     // episodes started (published by the next step)
-        rb.counters[2] += s_total;                                     // episodes completed
     }
     if (!flag) return;
     const int rank = s_prefix + s_warp_off[warp] + __popc(bal & ((1u << lane) - 1u));

@@ -28,15 +28,15 @@ __device__ __forceinline__ bool last_chunk_arrived(unsigned* ticket, unsigned n_
     return last;
 }
 
-// sum_{b < n} p[b * stride] in index order; the loads of a batch of 8 are independent (in flight together), the adds ordered
+// sum_{b < n} p[b * stride] in index order; the loads of a batch of 16 are independent (in flight together), the adds ordered
 __device__ __forceinline__ float ordered_sum(const float* __restrict__ p, size_t stride, unsigned n) {
     float sum = 0.f;
-    for (unsigned b0 = 0; b0 < n; b0 += 8) {
-        float v[8];
+    for (unsigned b0 = 0; b0 < n; b0 += 16) {
+        float v[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (b0 + k < n) ? __ldcg(p + (size_t)(b0 + k) * stride) : 0.f;
+        for (int k = 0; k < 16; ++k) v[k] = (b0 + k < n) ? __ldcg(p + (size_t)(b0 + k) * stride) : 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += v[k];
+        for (int k = 0; k < 16; ++k) sum += v[k];
     }
     return sum;
 }
@@ -132,6 +132,7 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, cons
     for (int e = threadIdx.x; e < A * d; e += blockDim.x) {
         const int a = e / d, c = e % d;
         float s = 0.f;
+#pragma unroll 16
         for (int r = 0; r < nt; ++r) s = fmaf(sdq[r][a], hh[(long long)(t0 + r) * d + c], s);
         part[(size_t)blockIdx.x * (A * d + A) + e] = s;
     }
@@ -410,8 +411,9 @@ __global__ void pos_bwd_kernel(const float* __restrict__ dx0, int B, int L, int 
 
 // obs embedding: continuous  gW[c,k] += sum_t dx0[t,c] obs[t,k];  discrete: through Embedding->Flatten->Linear.
 // 32 tokens per CTA.
-// Per-CTA partials [d*KI | d | vocab*E] summed in CTA order by the last CTA (no atomics; the table rows hit by several
-// tokens of a CTA are accumulated in token order).
+// Per-CTA partials [d*KI | d | vocab*E] summed in CTA order (no atomics; the table rows hit by several tokens of a CTA are
+// accumulated in token order).
+#define EMBED_INLINE_REDUCE_MAX 1024
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c, const float* __restrict__ params,
                  long long emb_table, long long emb_w, int L, int T, float* __restrict__ g_table,
@@ -472,7 +474,16 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
             mypart[d * KI + d + e] = s;
         }
     }
-    (void)ticket;                                             // the per-CTA partials are summed by embed_reduce_kernel
+    // few gradient elements (continuous observations: d*O + d): the last CTA sums the partials; the ~10 k elements of a
+    // discrete embedding go through embed_reduce_kernel (a single CTA walking 50 partial rows of each would serialise ~200 us)
+    if (n_part > EMBED_INLINE_REDUCE_MAX) return;
+    if (!last_chunk_arrived(ticket, gridDim.x)) return;
+    for (int e = threadIdx.x; e < n_part; e += blockDim.x) {
+        const float sum = ordered_sum(part + e, (size_t)n_part, gridDim.x);
+        if (e < d * KI) g_w[e] = sum;
+        else if (e < d * KI + d) g_b[e - d * KI] = sum;
+        else g_table[e - d * KI - d] = sum;
+    }
 }
 // CTA-ordered sum of the embedding-gradient partials: one thread per gradient element (the discrete embedding has ~10 k of
 // them: a single last CTA walking 50 partial rows of each would serialise ~200 us)
@@ -719,9 +730,11 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
                                                               grads + lay.emb_w, grads + lay.emb_b, s.psmall, s.ticket + 3);
         DTQN_LAUNCH_CHECK();
         const int n_part = d * KI + d + (cfg->discrete ? cfg->vocab * cfg->embed_per_obs : 0);
-        embed_reduce_kernel<<<dtqn_cdiv(n_part, 256), 256, 0, st>>>(s.psmall, dtqn_cdiv(T0, 32), n_part, d * KI, d, grads + lay.emb_w,
-                                                                    grads + lay.emb_b, cfg->discrete ? grads + lay.emb_table : nullptr);
-        DTQN_LAUNCH_CHECK();
+        if (n_part > EMBED_INLINE_REDUCE_MAX) {
+            embed_reduce_kernel<<<dtqn_cdiv(n_part, 256), 256, 0, st>>>(s.psmall, dtqn_cdiv(T0, 32), n_part, d * KI, d, grads + lay.emb_w,
+                                                                        grads + lay.emb_b, cfg->discrete ? grads + lay.emb_table : nullptr);
+            DTQN_LAUNCH_CHECK();
+        }
     }
     prof_end(PROF_OTHER, st, 0.0);
     return 0;

@@ -8,7 +8,6 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/r2_final_bench.json")); r=json.load(open("gpurun_out/r2_final_bench_reference.json"))
 print("ours", d["ms_per_step"], d["value"], d["grad_steps_per_sec"], "e2e", d["e2e"]["value"], "ref", r["value"], r["cpu_baseline"]["cores"], r["cpu_baseline"]["one_thread_value"])
-print(d["roofline"]["per_kernel_us_per_step"]); print(d["breakdown"]); print(d["sub_records"]); print(d["cpu_baseline"])
+print(d["roofline"]["per_kernel_us_per_step"]); print(d["breakdown"]); print(d["sub_records"])
 print({k:v for k,v in d["roofline"].items() if k in ("kernel","bound","achieved","peak","frac","avg_us_per_launch")})
 PY
-bash tools/ncu_round2.sh
