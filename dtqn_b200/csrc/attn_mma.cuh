@@ -123,3 +123,100 @@ __device__ __forceinline__ void att_head(const float* __restrict__ sq, int h, in
     if (L > 32) att_mtile<2>(sq, h, L, lane, out);
     if (L > 48) att_mtile<3>(sq, h, L, lane, out);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// General form for head_dim = 8 * KH (KH = 2: d_model 128 with 8 heads, the Memory-5 network): the q|k|v image has rows of
+// 3 * D floats (+ pad), head h occupies columns [h * HD, (h + 1) * HD) of each third.  Q K^T runs KH k-steps of 8 per block and
+// P V produces KH 8-column tiles, each with the same TF32 hi/lo split (3 MMAs per product) as above.
+template <int MT, int KH, int D, int LD, typename Out>
+__device__ __forceinline__ void att_mtile_g(const float* __restrict__ sq, int h, int L, int lane, Out&& out) {
+    constexpr int NB = 2 * MT + 2, HD = 8 * KH;
+    const int g = lane >> 2, t = lane & 3;
+    const int nb_l = (L + 7) >> 3;
+    const int r0 = 16 * MT;
+    uint32_t qh[KH][4], ql[KH][4];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+        const float* q0 = sq + (r0 + g) * LD + h * HD + 8 * kh + t;
+        att_split(q0[0], qh[kh][0], ql[kh][0]);
+        att_split(q0[8 * LD], qh[kh][1], ql[kh][1]);
+        att_split(q0[4], qh[kh][2], ql[kh][2]);
+        att_split(q0[8 * LD + 4], qh[kh][3], ql[kh][3]);
+    }
+    float s[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        s[b][0] = s[b][1] = s[b][2] = s[b][3] = 0.f;
+        if (b < nb_l) {
+#pragma unroll
+            for (int kh = 0; kh < KH; ++kh) {
+                const float* kp = sq + (8 * b + g) * LD + D + h * HD + 8 * kh + t;
+                uint32_t kh0, kl0, kh1, kl1;
+                att_split(kp[0], kh0, kl0);
+                att_split(kp[4], kh1, kl1);
+                att_mma(s[b], ql[kh], kh0, kh1);
+                att_mma(s[b], qh[kh], kl0, kl1);
+                att_mma(s[b], qh[kh], kh0, kh1);
+            }
+        }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (b < nb_l) {
+            if (b >= NB - 2) {
+                const int key = 8 * b + 2 * t, ra = r0 + g, rb = r0 + g + 8;
+                if (key > ra) s[b][0] = -INFINITY;
+                if (key + 1 > ra) s[b][1] = -INFINITY;
+                if (key > rb) s[b][2] = -INFINITY;
+                if (key + 1 > rb) s[b][3] = -INFINITY;
+            }
+            m0 = fmaxf(m0, fmaxf(s[b][0], s[b][1]));
+            m1 = fmaxf(m1, fmaxf(s[b][2], s[b][3]));
+        }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f, o[KH][4], o_lh[KH][4], o_hl[KH][4];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { o[kh][e] = 0.f; o_lh[kh][e] = 0.f; o_hl[kh][e] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (b < nb_l) {
+            const float p0 = att_ex2(s[b][0] - m0), p1 = att_ex2(s[b][1] - m0);
+            const float p2 = att_ex2(s[b][2] - m1), p3 = att_ex2(s[b][3] - m1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            uint32_t ph[4], pl[4];
+            att_split(p0, ph[0], pl[0]); att_split(p2, ph[1], pl[1]);
+            att_split(p1, ph[2], pl[2]); att_split(p3, ph[3], pl[3]);
+#pragma unroll
+            for (int kh = 0; kh < KH; ++kh) {
+                const float* vp = sq + (8 * b + 2 * t) * LD + 2 * D + h * HD + 8 * kh + g;
+                uint32_t vh0, vl0, vh1, vl1;
+                att_split(vp[0], vh0, vl0);
+                att_split(vp[LD], vh1, vl1);
+                att_mma(o_lh[kh], pl, vh0, vh1);
+                att_mma(o_hl[kh], ph, vl0, vl1);
+                att_mma(o[kh], ph, vh0, vh1);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+        out(r0 + g, h * HD + 8 * kh + 2 * t, (o[kh][0] + o_lh[kh][0] + o_hl[kh][0]) * i0, (o[kh][1] + o_lh[kh][1] + o_hl[kh][1]) * i0);
+        out(r0 + g + 8, h * HD + 8 * kh + 2 * t, (o[kh][2] + o_lh[kh][2] + o_hl[kh][2]) * i1, (o[kh][3] + o_lh[kh][3] + o_hl[kh][3]) * i1);
+    }
+}
+
+template <int KH, int D, int LD, typename Out>
+__device__ __forceinline__ void att_head_g(const float* __restrict__ sq, int h, int L, int lane, Out&& out) {
+    att_mtile_g<0, KH, D, LD>(sq, h, L, lane, out);
+    if (L > 16) att_mtile_g<1, KH, D, LD>(sq, h, L, lane, out);
+    if (L > 32) att_mtile_g<2, KH, D, LD>(sq, h, L, lane, out);
+    if (L > 48) att_mtile_g<3, KH, D, LD>(sq, h, L, lane, out);
+}

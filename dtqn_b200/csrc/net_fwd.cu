@@ -564,6 +564,37 @@ attn_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, flo
     }
 }
 
+// The same for d_model = 128 / 8 heads (head_dim 16, the Memory-5 network): q|k|v rows of 384 floats staged with a stride of
+// 388 (== 4 mod 32: conflict-free fragment loads), two k-steps per Q K^T block and two 8-column P V tiles per head.
+constexpr int ATT_LD128 = 3 * 128 + 4;
+__global__ void __launch_bounds__(256)
+attn_mma128_kernel(const float* __restrict__ qkv, float* __restrict__ o, int L, float scale) {
+    extern __shared__ float sm_kv[];                           // [64][ATT_LD128]
+    const size_t t0 = (size_t)blockIdx.x * L;
+    const int tid = threadIdx.x;
+    const float qs = scale * 1.4426950408889634f;
+    for (int e = tid; e < 64 * 96; e += 256) {
+        const int r = e / 96, c4 = (e % 96) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < L) {
+            v = __ldg(reinterpret_cast<const float4*>(qkv + (t0 + r) * 384 + c4));
+            if (c4 < 128) { v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs; }
+        }
+        *reinterpret_cast<float4*>(sm_kv + r * ATT_LD128 + c4) = v;
+    }
+    __syncthreads();
+    const int h = tid >> 5, lane = tid & 31;
+    float* sq = sm_kv;
+    att_head_g<2, 128, ATT_LD128>(sq, h, L, lane, [&](int row, int col, float v0, float v1) {
+        *reinterpret_cast<float2*>(sq + row * ATT_LD128 + col) = make_float2(v0, v1);   // parked in the consumed q columns
+    });
+    __syncthreads();
+    for (int e = tid; e < L * 32; e += 256) {
+        const int r = e >> 5, c4 = (e & 31) * 4;
+        *reinterpret_cast<float4*>(o + (t0 + r) * 128 + c4) = *reinterpret_cast<const float4*>(sm_kv + r * ATT_LD128 + c4);
+    }
+}
+
 // ---- acting: attention of the LAST valid query only (the policy reads q[:, -1, :], agents/dtqn.py:107) ------------------
 // ql [G*n_seq, d] = scaled-later query of the last valid token; kv [T, 2d] = (k | v) of every token.  One warp per
 // (sequence, head): lanes stride over the n_i keys, warp-shuffle softmax, then HD warp reductions for P V.
@@ -885,6 +916,15 @@ extern "C" int dtqn_forward(const dtqn_net_cfg* cfg, int32_t G, const float* con
                     attr_set = true;
                 }
                 attn_mma_kernel<<<(unsigned)(n_seq * G), 256, sm_mma, st>>>(la.qkv, la.o, L, scale);
+            } else if (g_attn_mma && !save && seq_kernel && hd == 16 && d == 128 && H == 8 && L <= 64) {   // inference groups only: the
+                // training forward keeps the exact-fp32 kernel (ReLU masks / gradients closest to the reference's)
+                const size_t sm_mma = sizeof(float) * 64 * ATT_LD128;
+                static bool attr_set128 = false;
+                if (!attr_set128) {
+                    cudaFuncSetAttribute(attn_mma128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mma);
+                    attr_set128 = true;
+                }
+                attn_mma128_kernel<<<(unsigned)(n_seq * G), 256, sm_mma, st>>>(la.qkv, la.o, L, scale);
             } else if (seq_kernel) {
                 if (hd == 8) {
                     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
