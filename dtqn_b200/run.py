@@ -4,8 +4,8 @@
     torchrun --nproc-per-node 8 -m dtqn_b200.run --envs DiscreteCarFlag-v0 --in-embed 64 --n-envs 4096
 
 One "timestep" of the reference loop (run.py:290) is one lockstep iteration here: every env takes one step and the agent
-takes one gradient step, so ``--num-steps`` iterations collect ``num-steps x n-envs x world`` transitions.  New flag (no
-reference analogue): ``--n-envs`` lockstep environments per GPU.  Every ``--eval-frequency`` iterations rank 0 logs the
+takes one gradient step, so ``--num-steps`` iterations collect ``num-steps x n-envs x world`` transitions.  New flags (no
+reference analogue): ``--n-envs`` lockstep environments per GPU, ``--record-every``, ``--updates-per-step``, ``--float-context``.  Every ``--eval-frequency`` iterations rank 0 logs the
 reference's keys (run.py:303-325) through ``dtqn_b200.logging_utils`` -- ``<policy_path>_results.csv`` / ``_losses.csv`` with
 ``--disable-wandb``, wandb otherwise -- and prints the ``--verbose`` line; ``--render`` is accepted and ignored.
 Checkpoint / resume follows run.py:452-499,337-352,526-529: the same ``policies/<project>/<env>/model=..._seed=N`` path
@@ -57,6 +57,13 @@ def get_args(argv=None):
     p.add_argument("--slurm-job-id", default=0, type=str)
     p.add_argument("--n-envs", type=int, default=4096, help="lockstep environments per GPU (new)")
     p.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    p.add_argument("--record-every", type=int, default=1,
+                   help="each env stores every K-th of its episodes in the replay (new): keeps the reference's replay horizon "
+                        "(~25 %% of the run) with thousands of envs per update; 1 = store everything")
+    p.add_argument("--updates-per-step", type=int, default=1, help="gradient updates per lockstep env step (new)")
+    p.add_argument("--float-context", action="store_true",
+                   help="keep float observations in the acting context instead of reproducing the reference's int64 context "
+                        "(utils/context.py:46 truncates CarFlag observations toward zero)")
     return p.parse_args(argv)
 
 
@@ -78,7 +85,8 @@ def run_experiment(args):
                         buf_size=max(args.buf_size, 8 * args.n_envs * 200), lr=args.lr, tuf=args.tuf,
                         gamma=args.discount, history=args.history, num_steps=args.num_steps, obs_embed=args.obs_embed,
                         pos=args.pos, max_episode_steps=args.max_episode_steps, a_embed=args.a_embed, dropout=args.dropout,
-                        identity=args.identity, gate=args.gate)
+                        identity=args.identity, gate=args.gate, record_every=args.record_every,
+                        updates_per_step=args.updates_per_step, trunc_context_obs=not args.float_context)
     rank = tr.rank
     if rank == 0:
         n = sum(p.numel() for p in tr.agent.policy_network.parameters())

@@ -80,10 +80,11 @@ def test_reference_written_checkpoint_unpickles_without_the_reference_package():
     import pickle
     import numpy as np
     import pytest
-    assert "utils.logging_utils" not in sys.modules
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refckpt")
     c = ck.read_checkpoint_file(os.path.join(d, "ref_checkpoint.pt"))
     z = np.load(os.path.join(d, "expect.npz"))
+    # the reference's RunningAverage objects come back as the loader's plain holder, whether or not the reference package is importable
+    assert type(c["td_errors"]) is ck._RefRunningAverage and type(c["episode_successes"]) is ck._RefRunningAverage
     assert c["step"] == int(z["meta"][5]) and c["replay_buffer_pos"] == [int(z["replay_pos"][0]), 0]
     assert abs(c["epsilon"] - float(z["epsilon"][0])) == 0.0
     assert abs(ck.RunningAverage.from_state(c["td_errors"]).mean() - float(z["td_errors_mean"][0])) < 1e-9
