@@ -24,7 +24,7 @@ struct VarLayer {
 struct VarAct {
     float* x0;
     VarLayer layer[DTQN_MAX_LAYERS];
-    float *hh, *q, *tmp, *tmp2;                              // tmp: [T, d] GEMM staging (gate pre-activations), tmp2 likewise
+    float *hh, *tmp;                                         // tmp: [T, d] rows of the last valid position (acting)
     long long total;
 };
 
@@ -42,7 +42,7 @@ long long var_act_layout(const dtqn_net_cfg& c, long long T, float* base, VarAct
             for (VarGate* g : {&l.g1, &l.g2}) { g->z = take(T * d); g->r = take(T * d); g->hg = take(T * d); g->rx = take(T * d); }
         }
     }
-    A.hh = take(T * d); A.q = take(T * c.num_actions); A.tmp = take(T * d); A.tmp2 = take(T * d);
+    A.hh = take(T * d); A.tmp = take(T * d);
     A.total = o;
     return o;
 }
@@ -764,9 +764,9 @@ int var_td_backward(const dtqn_net_cfg& c, const NetLayout& lay, const float* pa
     // over the layers that share the gate (`first` = first application in this backward pass)
     auto gate_bwd = [&](int k, bool first, const float* du, const float* x, const float* y, const VarGate& gs, float* dx, float* dy) -> int {
         if (!c.gate_gru) {                                     // ResGate: both inputs receive du
-            cudaMemcpyAsync(dx, du, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(dy, du, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
-            return 0;
+            cudaError_t e1 = cudaMemcpyAsync(dx, du, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
+            cudaError_t e2 = cudaMemcpyAsync(dy, du, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
+            return e1 != cudaSuccess ? (int)e1 : (int)e2;
         }
         const GateOff& q = lay.gate[k];
         const int acc = first ? 0 : 1;
@@ -831,7 +831,7 @@ int var_td_backward(const dtqn_net_cfg& c, const NetLayout& lay, const float* pa
         // gradient w.r.t. u1 in s.gu
         if (c.identity) {                                      // ffn_in = LN2(u1); u1 also feeds the gate's skip input (s.ga)
             if ((rc = var_dgrad<E_NONE>(s.gh, params + lo.f1_w, nullptr, s.gb, T0, 4 * d, d, 0, st))) return rc;
-            cudaMemcpyAsync(s.gu, s.ga, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
+            if (cudaError_t ce = cudaMemcpyAsync(s.gu, s.ga, sizeof(float) * n, cudaMemcpyDeviceToDevice, st)) return (int)ce;
             if ((rc = ln_bwd(s.gb, la.u1, la.stB, lo.ln2_w, lo.ln2_b, s.gu, 1))) return rc;
         } else {                                               // ffn_in = lnA = LN1(u1), which is also the gate's skip input
             if ((rc = var_dgrad<E_ADD>(s.gh, params + lo.f1_w, s.ga, s.gb, T0, 4 * d, d, 0, st))) return rc;
@@ -859,7 +859,7 @@ int var_td_backward(const dtqn_net_cfg& c, const NetLayout& lay, const float* pa
         if ((rc = var_wgrad(s.gqkv, att_in, T0, 3 * d, d, grads + lo.in_w, grads + lo.in_b, 0, st))) return rc;
         if (c.identity) {                                      // att_in = LN1(x_in); x_in also gets the gate's skip gradient
             if ((rc = var_dgrad<E_NONE>(s.gqkv, params + lo.in_w, nullptr, s.gb, T0, 3 * d, d, 0, st))) return rc;
-            cudaMemcpyAsync(s.gx, s.ga, sizeof(float) * n, cudaMemcpyDeviceToDevice, st);
+            if (cudaError_t ce = cudaMemcpyAsync(s.gx, s.ga, sizeof(float) * n, cudaMemcpyDeviceToDevice, st)) return (int)ce;
             if ((rc = ln_bwd(s.gb, x_in, la.stA, lo.ln1_w, lo.ln1_b, s.gx, 1))) return rc;
         } else {
             if ((rc = var_dgrad<E_ADD>(s.gqkv, params + lo.in_w, s.ga, s.gx, T0, 3 * d, d, 0, st))) return rc;
