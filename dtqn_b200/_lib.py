@@ -66,6 +66,8 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    # opt-in: programmatic dependent launch for the training chain (csrc/common.cuh launch_k); off by default
+    lib.dtqn_set_pdl(C.c_int32(1 if os.environ.get("DTQN_B200_PDL", "0") == "1" else 0))
     return lib
 
 

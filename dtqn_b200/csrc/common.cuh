@@ -27,3 +27,24 @@ __device__ __forceinline__ float warp_min(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ---- programmatic dependent launch (opt-in, dtqn_set_pdl) ------------------------------------------------------------------------
+// The training step is a chain of ~27 small dependent kernels; with the launch attribute below the next kernel's CTAs are
+// scheduled while the previous kernel drains and block in pdl_sync() (griddepcontrol.wait) until it has completed and its
+// writes are visible -- same ordering as plain stream order, without the dependency latency between the two grids.
+// Every kernel launched through launch_k() MUST call pdl_sync() before touching global memory.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -48,6 +48,7 @@ td_loss_kernel(const float* __restrict__ q_all, const uint8_t* __restrict__ act_
                const uint8_t* __restrict__ done, int B, int L, int A, int history, float gamma,
                float* __restrict__ dq, float* __restrict__ partial, unsigned* __restrict__ ticket,
                float* __restrict__ stats) {
+    pdl_sync();
     const long long T = (long long)B * L;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float se = 0.f, qs = 0.f, ys = 0.f, qmx = -INFINITY, qmn = INFINITY, ymx = -INFINITY, ymn = INFINITY;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, const float* __restrict__ W2, int T, int d,
                 int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2,
                 float* __restrict__ part, unsigned* __restrict__ ticket) {
+    pdl_sync();
     __shared__ float sdq[HB_TOK][33];
     const int t0 = blockIdx.x * HB_TOK;
     const int nt = min(HB_TOK, T - t0);
@@ -155,6 +157,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ aux,
              float* __restrict__ dX, int T, int Nf, int Kf) {
+    pdl_sync();
     __shared__ GemmSmem<BN> sm;
     constexpr int TN = BN / 16;
     const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
@@ -236,6 +239,7 @@ wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, i
 struct WgradSegs { long long begin[DTQN_MAX_LAYERS + 1], len4[DTQN_MAX_LAYERS + 1]; int n; long long total4; };
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, long long pstride, int n_chunks, WgradSegs segs, float* __restrict__ grads) {
+    pdl_sync();
     long long q = (long long)blockIdx.x * 256 + threadIdx.x;
     if (q >= segs.total4) return;
     int sgi = 0;
@@ -262,6 +266,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xin, const
               const float* __restrict__ st, const float* __restrict__ gamma, int T, float* __restrict__ du,
               float* __restrict__ da, float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ part,
               unsigned* __restrict__ ticket) {
+    pdl_sync();
     constexpr int PER = D / 32, ROWS = 4;                     // rows per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gam[PER], ag[PER], ab[PER];
@@ -313,6 +318,7 @@ template <int HD>
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ d_o,
                 float* __restrict__ d_qkv, int L, int d, float scale) {
+    pdl_sync();
     __shared__ float Qs[128][HD + 1], Ks[128][HD + 1], Vs[128][HD + 1], Gs[128][HD + 1];
     __shared__ float sm_m[128], sm_il[128], sm_D[128];
     const int h = blockIdx.x;
@@ -402,6 +408,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, cons
 // ---- embedding backward ------------------------------------------------------------------------------------------------------------
 // position table: gpos[j, c] = sum_b dx0[b, j, c]   (one thread per (j, c), no atomics)
 __global__ void pos_bwd_kernel(const float* __restrict__ dx0, int B, int L, int d, float* __restrict__ gpos) {
+    pdl_sync();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L * d) return;
     float s = 0.f;
@@ -418,6 +425,7 @@ __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c, const float* __restrict__ params,
                  long long emb_table, long long emb_w, int L, int T, float* __restrict__ g_table,
                  float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ part, unsigned* __restrict__ ticket) {
+    pdl_sync();
     extern __shared__ float smem[];
     const int d = c.d_model, O = c.obs_dim, E = c.discrete ? c.embed_per_obs : 1, KI = O * E;
     const int n_tab = c.discrete ? c.vocab * E : 0, n_part = d * KI + d + n_tab;
@@ -490,6 +498,7 @@ embed_bwd_kernel(const float* __restrict__ dx0, dtqn_obs_src src, dtqn_net_cfg c
 __global__ void __launch_bounds__(256)
 embed_reduce_kernel(const float* __restrict__ part, int n_blocks, int n_part, int n_w, int n_b, float* __restrict__ g_w,
                     float* __restrict__ g_b, float* __restrict__ g_table) {
+    pdl_sync();
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= n_part) return;
     const float sum = ordered_sum(part + e, (size_t)n_part, (unsigned)n_blocks);
@@ -532,8 +541,8 @@ template <int EPI>
 int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
     dim3 grid(dtqn_cdiv(T, GEMM_BM), 1, 1);
     prof_begin(PROF_DGRAD, st);
-    if (Kf % 128 == 0) { grid.y = Kf / 128; dgrad_kernel<128, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
-    else if (Kf % 64 == 0) { grid.y = Kf / 64; dgrad_kernel<64, EPI><<<grid, GEMM_THREADS, 0, st>>>(dY, W, aux, dX, T, Nf, Kf); }
+    if (Kf % 128 == 0) { grid.y = Kf / 128; launch_k(dgrad_kernel<128, EPI>, grid, GEMM_THREADS, 0, st, dY, W, aux, dX, T, Nf, Kf); }
+    else if (Kf % 64 == 0) { grid.y = Kf / 64; launch_k(dgrad_kernel<64, EPI>, grid, GEMM_THREADS, 0, st, dY, W, aux, dX, T, Nf, Kf); }
     else return DTQN_E_UNSUPPORTED;
     prof_end(PROF_DGRAD, st, 2.0 * (double)T * Nf * Kf);
     DTQN_LAUNCH_CHECK();
@@ -632,14 +641,14 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     if (ce != cudaSuccess) return (int)ce;
 
     prof_begin(PROF_TD, st);
-    td_loss_kernel<<<dtqn_cdiv(T0, 256), 256, 0, st>>>(q_all, act_win, rew, done, B, L, A, history, gamma, s.dq,
-                                                        s.partial, s.ticket, stats_out);
+    launch_k(td_loss_kernel, dtqn_cdiv(T0, 256), 256, 0, st, q_all, act_win, rew, done, B, L, A, history, gamma, s.dq, s.partial,
+             s.ticket, stats_out);
     prof_end(PROF_TD, st, 0.0);
     DTQN_LAUNCH_CHECK();
     // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
     prof_begin(PROF_HEAD, st);
-    head_bwd_kernel<<<dtqn_cdiv(T0, HB_TOK), 256, 0, st>>>(s.dq, act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
-                                                        grads + lay.h2_w, grads + lay.h2_b, s.psmall, s.ticket + 1);
+    launch_k(head_bwd_kernel, dtqn_cdiv(T0, HB_TOK), 256, 0, st, s.dq, (const float*)act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
+             grads + lay.h2_w, grads + lay.h2_b, s.psmall, s.ticket + 1);
     prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();
     g_side.init();
@@ -660,8 +669,8 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         const float* x_in = li == 0 ? act.x0 : act.layer[li - 1].x2;
         // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
         prof_begin(PROF_LN_BWD, st);
-        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
-        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
+        if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
+        else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // ffn.2
@@ -674,8 +683,8 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
         // LN1 backward: dy = gx1 -> gu (du1), ga1 (d out_proj output)
         prof_begin(PROF_LN_BWD, st);
-        if (d == 64) ln_bwd_kernel<64><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
-        else         ln_bwd_kernel<128><<<dtqn_cdiv(T0, 32), 256, 0, st>>>(s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
+        if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
+        else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
         prof_end(PROF_LN_BWD, st, 0.0);
         DTQN_LAUNCH_CHECK();
         // out_proj
@@ -688,9 +697,9 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
             const int thr = L <= 64 ? 64 : 128;
             const float scale = 1.0f / sqrtf((float)hd);
             prof_begin(PROF_ATTN_BWD, st);
-            if (hd == 8) attn_bwd_kernel<8><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
-            else if (hd == 16) attn_bwd_kernel<16><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
-            else if (hd == 4) attn_bwd_kernel<4><<<grid, thr, 0, st>>>(la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            if (hd == 8) launch_k(attn_bwd_kernel<8>, grid, thr, 0, st, la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            else if (hd == 16) launch_k(attn_bwd_kernel<16>, grid, thr, 0, st, la.qkv, la.o, s.go, s.gqkv, L, d, scale);
+            else if (hd == 4) launch_k(attn_bwd_kernel<4>, grid, thr, 0, st, la.qkv, la.o, s.go, s.gqkv, L, d, scale);
             else return DTQN_E_UNSUPPORTED;
             prof_end(PROF_ATTN_BWD, st, 8.0 * (double)T0 * L * d);
             DTQN_LAUNCH_CHECK();
@@ -712,27 +721,26 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         }
         segs.n = cfg->n_layers + 1; segs.total4 = tot;
         prof_begin(PROF_WGRAD, st);
-        wgrad_reduce_kernel<<<dtqn_cdiv(tot, 256), 256, 0, st>>>(s.pgrad, lay.total, dtqn_cdiv(Ti, g_wgrad_chunk), segs, grads);
+        launch_k(wgrad_reduce_kernel, dtqn_cdiv(tot, 256), 256, 0, st, (const float*)s.pgrad, lay.total, dtqn_cdiv(Ti, g_wgrad_chunk), segs, grads);
         prof_end(PROF_WGRAD, st, 0.0);
         DTQN_LAUNCH_CHECK();
     }
     // embedding + position table
     prof_begin(PROF_OTHER, st);
     if (cfg->pos_trainable) {
-        pos_bwd_kernel<<<dtqn_cdiv((long long)L * d, 256), 256, 0, st>>>(s.gx, B, L, d, grads + lay.pos);
+        launch_k(pos_bwd_kernel, dtqn_cdiv((long long)L * d, 256), 256, 0, st, (const float*)s.gx, B, L, d, grads + lay.pos);
         DTQN_LAUNCH_CHECK();
     }
     {
         const int KI = lay.k_in;
         const size_t smem = sizeof(float) * (32 * d + 32 * KI) + sizeof(int) * 32 * cfg->obs_dim;
-        embed_bwd_kernel<<<dtqn_cdiv(T0, 32), 256, smem, st>>>(s.gx, *obs_src, *cfg, params, lay.emb_table, lay.emb_w, L, Ti,
-                                                              cfg->discrete ? grads + lay.emb_table : nullptr,
-                                                              grads + lay.emb_w, grads + lay.emb_b, s.psmall, s.ticket + 3);
+        launch_k(embed_bwd_kernel, dtqn_cdiv(T0, 32), 256, smem, st, (const float*)s.gx, *obs_src, *cfg, params, lay.emb_table, lay.emb_w,
+                 L, Ti, cfg->discrete ? grads + lay.emb_table : nullptr, grads + lay.emb_w, grads + lay.emb_b, s.psmall, s.ticket + 3);
         DTQN_LAUNCH_CHECK();
         const int n_part = d * KI + d + (cfg->discrete ? cfg->vocab * cfg->embed_per_obs : 0);
         if (n_part > EMBED_INLINE_REDUCE_MAX) {
-            embed_reduce_kernel<<<dtqn_cdiv(n_part, 256), 256, 0, st>>>(s.psmall, dtqn_cdiv(T0, 32), n_part, d * KI, d, grads + lay.emb_w,
-                                                                        grads + lay.emb_b, cfg->discrete ? grads + lay.emb_table : nullptr);
+            launch_k(embed_reduce_kernel, dtqn_cdiv(n_part, 256), 256, 0, st, (const float*)s.psmall, dtqn_cdiv(T0, 32), n_part, d * KI, d,
+                     grads + lay.emb_w, grads + lay.emb_b, cfg->discrete ? grads + lay.emb_table : nullptr);
             DTQN_LAUNCH_CHECK();
         }
     }

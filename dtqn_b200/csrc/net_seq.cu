@@ -279,6 +279,7 @@ __device__ __forceinline__ void sq_res_ln(const float (&acc)[4][4], const float*
 
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 seq_forward_kernel(SeqFwdArgs a) {
+    pdl_sync();
     extern __shared__ __align__(16) uint8_t sq_raw[];
     SeqSmem& sm = *reinterpret_cast<SeqSmem*>(sq_raw);
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -411,7 +412,7 @@ int launch_seq_forward(const dtqn_net_cfg& c, const NetLayout& lay, const NetAct
         attr_set = true;
     }
     prof_begin(PROF_SEQ_FWD, st);
-    seq_forward_kernel<<<G * n_seq, SQ_THREADS, sizeof(SeqSmem), st>>>(a);
+    launch_k(seq_forward_kernel, G * n_seq, SQ_THREADS, sizeof(SeqSmem), st, a);
     prof_end(PROF_SEQ_FWD, st, 2.0 * (double)G * n_seq * L * (c.n_layers * 12.0 * SQ_D * SQ_D + SQ_D * SQ_D + SQ_D * c.num_actions));
     DTQN_LAUNCH_CHECK();
     return 0;

@@ -12,6 +12,7 @@ namespace {
 
 __global__ void __launch_bounds__(OPT_THREADS)
 sqnorm_kernel(const float* __restrict__ g, long long n, float scale, float* __restrict__ partial, long long* step) {
+    pdl_sync();
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * OPT_THREADS) {
         const float v = g[i] * scale;
@@ -34,6 +35,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
                  long long n, float scale, float max_norm, float lr, float beta1, float beta2, float eps,
                  long long* __restrict__ step, const float* __restrict__ partial, int n_partial,
                  float* __restrict__ stats, int* __restrict__ flags, float* __restrict__ ring, int ring_len) {
+    pdl_sync();
     __shared__ float s_coef;
     __shared__ int s_bad;
     if (threadIdx.x == 0) {
@@ -83,8 +85,8 @@ int launch_clip_adam_only(float* params, const float* grads, float* exp_avg, flo
     int blocks = dtqn_cdiv(n, OPT_THREADS * 4);
     if (blocks > OPT_MAX_BLOCKS) blocks = OPT_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
-    clip_adam_kernel<<<blocks, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1,
-                                                    beta2, eps, step, partial, n_partial, stats, flags, ring, ring_len);
+    launch_k(clip_adam_kernel, blocks, OPT_THREADS, 0, st, params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1, beta2,
+             eps, step, partial, n_partial, stats, flags, ring, ring_len);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -100,11 +102,11 @@ extern "C" int dtqn_clip_adam(float* params, float* grads, float* exp_avg, float
     if (blocks > OPT_MAX_BLOCKS) blocks = OPT_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
     prof_begin(PROF_ADAM, st);
-    sqnorm_kernel<<<blocks, OPT_THREADS, 0, st>>>(grads, n, grad_scale, scratch, (long long*)step_counter);
+    launch_k(sqnorm_kernel, blocks, OPT_THREADS, 0, st, (const float*)grads, (long long)n, grad_scale, scratch, (long long*)step_counter);
     DTQN_LAUNCH_CHECK();
-    clip_adam_kernel<<<blocks, OPT_THREADS, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, grad_scale, max_norm, lr, beta1,
-                                                    beta2, eps, (long long*)step_counter, scratch, blocks,
-                                                    stats_out, flags_out, stats_ring, stats_ring ? ring_len : 1);
+    launch_k(clip_adam_kernel, blocks, OPT_THREADS, 0, st, params, (const float*)grads, exp_avg, exp_avg_sq, (long long)n, grad_scale,
+             max_norm, lr, beta1, beta2, eps, (long long*)step_counter, (const float*)scratch, blocks, stats_out, flags_out,
+             stats_ring, stats_ring ? ring_len : 1);
     prof_end(PROF_ADAM, st, 32.0 * (double)n);     // 28 B/param Adam + 4 B/param norm pass
     DTQN_LAUNCH_CHECK();
     return 0;

@@ -48,3 +48,6 @@ extern "C" int dtqn_profile_read(int32_t tag, double* total_ms, int64_t* launche
     *total_ms = ms; *launches = n; *total_work = work;
     return 0;
 }
+
+int g_pdl = 0;
+extern "C" int dtqn_set_pdl(int32_t on) { g_pdl = on ? 1 : 0; return 0; }

@@ -33,6 +33,7 @@ __device__ __forceinline__ uint32_t bounded_ctr(uint64_t key, uint32_t& ctr, uin
 __global__ void __launch_bounds__(256)
 sample_indices_kernel(dtqn_replay rb, int batch, uint64_t seed, uint64_t draw, uint64_t* draw_counter,
                       int32_t* episodes, int32_t* starts) {
+    pdl_sync();
     const uint64_t d = draw + (draw_counter ? *draw_counter : 0ull);
     long long started = rb.counters[1];
     const uint32_t range = (uint32_t)(started < rb.n_slots ? started : rb.n_slots);
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(128)
 replay_gather_kernel(dtqn_replay rb, const int32_t* __restrict__ episodes, const int32_t* __restrict__ starts,
                      float* __restrict__ obs_win, uint8_t* __restrict__ act_win, float* __restrict__ rew,
                      uint8_t* __restrict__ done, int32_t* __restrict__ eplen) {
+    pdl_sync();
     const int b = blockIdx.x;
     const int e = episodes[b], s0 = starts[b];
     const int L = rb.context_len, O = rb.obs_dim, E = rb.max_episode_steps;
@@ -89,7 +91,7 @@ extern "C" int dtqn_replay_sample_indices(const dtqn_replay* rb, int32_t batch, 
     if (!rb || batch <= 0 || !episodes_out || !starts_out || !rb->counters || !rb->slot_open || !rb->episode_lengths)
         return DTQN_E_ARG;
     prof_begin(PROF_OTHER, (cudaStream_t)stream);
-    sample_indices_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*rb, batch, seed, draw, draw_counter, episodes_out, starts_out);
+    launch_k(sample_indices_kernel, 1, 256, 0, (cudaStream_t)stream, *rb, batch, seed, draw, draw_counter, episodes_out, starts_out);
     prof_end(PROF_OTHER, (cudaStream_t)stream, 0.0);
     DTQN_LAUNCH_CHECK();
     return 0;
@@ -104,7 +106,7 @@ extern "C" int dtqn_replay_gather(const dtqn_replay* rb, int32_t batch, const in
     const double L = rb->context_len, O = rb->obs_dim;
     const double win_bytes = 2.0 * ((L + 1) * O * 4 + (L + 1) + 4 * L + L) + 1.0;
     prof_begin(PROF_GATHER, (cudaStream_t)stream);
-    replay_gather_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(*rb, episodes, starts, obs_win, act_win, rew, done, eplen);
+    launch_k(replay_gather_kernel, batch, 128, 0, (cudaStream_t)stream, *rb, episodes, starts, obs_win, act_win, rew, done, eplen);
     prof_end(PROF_GATHER, (cudaStream_t)stream, win_bytes * batch);
     DTQN_LAUNCH_CHECK();
     return 0;

@@ -273,6 +273,11 @@ int dtqn_set_parallel_wgrad(int32_t on);
 /* Tokens per split-K chunk of the weight-gradient GEMMs (default 128, multiple of 16, >= 64): each chunk's partial tile is
  * stored and the last CTA of a tile adds the chunks in order (deterministic; no fp32 atomics). */
 int dtqn_set_wgrad_chunk(int32_t tokens);
+/* 1: the dependent kernels of the training step (sample, gather, forward, TD loss, backward chain, clip + Adam) are launched
+ * with the programmatic-stream-serialization attribute and block in griddepcontrol.wait until their predecessor has
+ * completed -- same results, the next grid is scheduled while the previous one drains.  0 (default): plain stream order.
+ * No reference analogue (launch-mechanism knob). */
+int dtqn_set_pdl(int32_t on);
 
 /* clip_grad_norm_(params, max_norm, error_if_nonfinite=True) + Adam.step (dtqn/agents/dtqn.py:257-265,
  * dtqn/agents/dqn.py:64): grads *= grad_scale (1/world after the allreduce), total = ||grads||_2,
