@@ -68,6 +68,11 @@ def _load():
         fn.restype = C.c_int
     # opt-in: programmatic dependent launch for the training chain (csrc/common.cuh launch_k); off by default
     lib.dtqn_set_pdl(C.c_int32(1 if os.environ.get("DTQN_B200_PDL", "0") == "1" else 0))
+    # launch-shape overrides of the backward pass (defaults are compiled in; see include/dtqn_b200.h)
+    for var, fn in (("DTQN_B200_DGRAD_ROWS", lib.dtqn_set_dgrad_rows), ("DTQN_B200_FUSE_LN_BWD", lib.dtqn_set_fuse_ln_bwd),
+                    ("DTQN_B200_HEAD_BWD_TOKENS", lib.dtqn_set_head_bwd_tokens)):
+        if var in os.environ and fn(C.c_int32(int(os.environ[var]))) != 0:
+            raise DtqnLibError(f"{var}={os.environ[var]}: unsupported value")
     return lib
 
 

@@ -108,18 +108,19 @@ td_loss_kernel(const float* __restrict__ q_all, const uint8_t* __restrict__ act_
 }
 
 // ---- head (ffn.2) backward: N = A is tiny -> CUDA cores --------------------------------------------------------------------
-// d_hh = (dq W2) * [hh > 0];  dW2 = dq^T hh;  db2 = colsum(dq).   HB_TOK tokens per CTA; per-CTA partials [A*d + A] summed in
-// CTA order by the last CTA.
+// d_hh = (dq W2) * [hh > 0];  dW2 = dq^T hh;  db2 = colsum(dq).   tok <= HB_TOK tokens per CTA (dtqn_set_head_bwd_tokens);
+// per-CTA partials [A*d + A] summed in CTA order by the last CTA.
 #define HB_TOK 64
+#define HB_TOK_MIN 16
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, const float* __restrict__ W2, int T, int d,
-                int A, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2,
+                int A, int tok, float* __restrict__ d_hh, float* __restrict__ gW2, float* __restrict__ gb2,
                 float* __restrict__ part, unsigned* __restrict__ ticket) {
     pdl_sync();
     __shared__ float sdq[HB_TOK][33];
-    const int t0 = blockIdx.x * HB_TOK;
-    const int nt = min(HB_TOK, T - t0);
-    for (int e = threadIdx.x; e < HB_TOK * A; e += blockDim.x) {
+    const int t0 = blockIdx.x * tok;
+    const int nt = min(tok, T - t0);
+    for (int e = threadIdx.x; e < tok * A; e += blockDim.x) {
         const int r = e / A, a = e % A;
         sdq[r][a] = r < nt ? dq[(long long)(t0 + r) * A + a] : 0.f;
     }
@@ -153,20 +154,33 @@ head_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ hh, cons
 // ---- dgrad:  dX[T, Kf] = dY[T, Nf] W[Nf, Kf]  (+ epilogue) -----------------------------------------------------------------
 enum { DG_NONE = 0, DG_MASK = 1, DG_ADD = 2 };
 
-template <int BN, int EPI>
+// BM rows per CTA (64 / 32 / 16; dtqn_set_dgrad_rows): with 1 600 tokens the 64-row tile fills 25 of 148 SMs.
+// LN = true (needs Kf == BN, one CTA per row block): the tile is the dy of the LayerNorm the forward pass applied to this
+// Linear's input (y = LN(x_in + relu(a))), and the epilogue is that LayerNorm's backward -- the ln_bwd_kernel maths on the
+// tile staged in shared memory -- so dX is never written:  du -> ln.du (may alias aux: rows are CTA-private and the aux reads
+// precede the barrier),  da = du * [r > 0] -> ln.da,  dgamma / dbeta per-CTA partials summed in CTA order by the last CTA.
+struct LnBwdArgs {
+    const float *xin, *r, *st, *gamma;
+    float *du, *da, *ggamma, *gbeta, *part;
+    unsigned* ticket;
+};
+
+template <int BM, int BN, int EPI, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS)
 dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ aux,
-             float* __restrict__ dX, int T, int Nf, int Kf) {
+             float* __restrict__ dX, int T, int Nf, int Kf, LnBwdArgs ln) {
     pdl_sync();
-    __shared__ GemmSmem<BN> sm;
-    constexpr int TN = BN / 16;
-    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
-    float acc[4][TN];
-    gemm_tile_64<BN, true>(dY, Nf, T, W, Kf, Nf, m0, n0, acc, sm);
+    __shared__ __align__(16) GemmSmem<BN> sm;
+    constexpr int RM = BM / 16, TN = BN / 16;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    float acc[RM][TN];
+    gemm_tile<BM, BN, true>(dY, Nf, T, W, Kf, Nf, m0, n0, acc, sm);
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    static_assert(!LN || BM * (BN + 1) <= (int)(sizeof(GemmSmem<BN>) / sizeof(float)), "dy tile must fit the GEMM slabs");
+    float* sY = reinterpret_cast<float*>(&sm);                 // LN: [BM][BN + 1] dy tile (the k loop ended with a barrier)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int lr = ty * RM + i, r = m0 + lr;
         if (r >= T) continue;
 #pragma unroll
         for (int j4 = 0; j4 < TN / 4; ++j4) {
@@ -178,7 +192,59 @@ dgrad_kernel(const float* __restrict__ dY, const float* __restrict__ W, const fl
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = (EPI == DG_MASK) ? (xv[q] > 0.f ? v[q] : 0.f) : v[q] + xv[q];
             }
-            *reinterpret_cast<float4*>(dX + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if constexpr (LN) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sY[lr * (BN + 1) + j4 * 64 + tx * 4 + q] = v[q];
+            } else {
+                *reinterpret_cast<float4*>(dX + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    if constexpr (LN) {
+        constexpr int D = BN, PER = D / 32, ROWS = BM / 8;     // rows per warp
+        __shared__ float sg[8][D], sb[8][D];
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float gam[PER], ag[PER], ab[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { gam[k] = ln.gamma[lane + 32 * k]; ag[k] = 0.f; ab[k] = 0.f; }
+        for (int rr = 0; rr < ROWS; ++rr) {
+            const int lr = warp * ROWS + rr, t = m0 + lr;
+            if (t >= T) break;
+            const float mean = ln.st[2 * t], rstd = ln.st[2 * t + 1];
+            float xh[PER], g[PER], rv[PER];
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const size_t o = (size_t)t * D + lane + 32 * k;
+                const float dyv = sY[lr * (BN + 1) + lane + 32 * k];
+                rv[k] = ln.r[o];
+                xh[k] = (ln.xin[o] + rv[k] - mean) * rstd;
+                g[k] = dyv * gam[k];
+                m1 += g[k]; m2 = fmaf(g[k], xh[k], m2);
+                ag[k] = fmaf(dyv, xh[k], ag[k]); ab[k] += dyv;
+            }
+            m1 = warp_sum(m1) * (1.f / D); m2 = warp_sum(m2) * (1.f / D);
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const size_t o = (size_t)t * D + lane + 32 * k;
+                const float v = rstd * (g[k] - m1 - xh[k] * m2);
+                ln.du[o] = v;
+                ln.da[o] = rv[k] > 0.f ? v : 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { sg[warp][lane + 32 * k] = ag[k]; sb[warp][lane + 32 * k] = ab[k]; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += blockDim.x) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int w = 0; w < 8; ++w) { s1 += sg[w][c]; s2 += sb[w][c]; }
+            ln.part[(size_t)blockIdx.x * 2 * D + c] = s1; ln.part[(size_t)blockIdx.x * 2 * D + D + c] = s2;
+        }
+        if (!last_chunk_arrived(ln.ticket, gridDim.x)) return;
+        for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+            const float sum = ordered_sum(ln.part + c, (size_t)(2 * D), gridDim.x);
+            if (c < D) ln.ggamma[c] = sum; else ln.gbeta[c - D] = sum;
         }
     }
 }
@@ -537,14 +603,46 @@ SideStream g_side;
 int g_parallel_wgrad = 1;
 int g_wgrad_chunk = 2 * WG_CHUNK;  // tokens per split-K chunk of the weight-gradient GEMMs (multiple of 16, >= WG_CHUNK); 128 measured best
 
+// Defaults = the fastest setting of tools/tune_bwd.py on the bench shape (32 x 50 tokens; profiles/r2_tune_bwd.txt: training
+// half 0.281 -> 0.249 ms against 64 rows / unfused / 64 tokens), and the one the network parity tests ran under.
+int g_head_tok = HB_TOK_MIN;        // tokens per CTA of head_bwd_kernel (dtqn_set_head_bwd_tokens)
+int g_dgrad_rows = 32;              // rows per CTA of the dgrad GEMMs (dtqn_set_dgrad_rows)
+int g_fuse_ln_bwd = 1;              // LayerNorm backward as the epilogue of the dgrad that produces its dy (dtqn_set_fuse_ln_bwd)
+
+template <int BM, int BN, int EPI, bool LN>
+void launch_dgrad_tile(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, const LnBwdArgs& ln,
+                       cudaStream_t st) {
+    launch_k(dgrad_kernel<BM, BN, EPI, LN>, dim3(dtqn_cdiv(T, BM), Kf / BN, 1), GEMM_THREADS, 0, st, dY, W, aux, dX, T, Nf, Kf, ln);
+}
+template <int BN, int EPI, bool LN>
+void launch_dgrad_rows(int rows, const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf,
+                       const LnBwdArgs& ln, cudaStream_t st) {
+    if (LN && BN == 128 && rows == 64) rows = 32;              // the 64 x 129 dy tile does not fit the GEMM slabs
+    if (rows == 16) launch_dgrad_tile<16, BN, EPI, LN>(dY, W, aux, dX, T, Nf, Kf, ln, st);
+    else if (rows == 32) launch_dgrad_tile<32, BN, EPI, LN>(dY, W, aux, dX, T, Nf, Kf, ln, st);
+    else if constexpr (!(LN && BN == 128)) launch_dgrad_tile<64, BN, EPI, LN>(dY, W, aux, dX, T, Nf, Kf, ln, st);
+}
+
 template <int EPI>
 int launch_dgrad(const float* dY, const float* W, const float* aux, float* dX, int T, int Nf, int Kf, cudaStream_t st) {
-    dim3 grid(dtqn_cdiv(T, GEMM_BM), 1, 1);
+    const LnBwdArgs none{};
     prof_begin(PROF_DGRAD, st);
-    if (Kf % 128 == 0) { grid.y = Kf / 128; launch_k(dgrad_kernel<128, EPI>, grid, GEMM_THREADS, 0, st, dY, W, aux, dX, T, Nf, Kf); }
-    else if (Kf % 64 == 0) { grid.y = Kf / 64; launch_k(dgrad_kernel<64, EPI>, grid, GEMM_THREADS, 0, st, dY, W, aux, dX, T, Nf, Kf); }
+    if (Kf % 128 == 0) launch_dgrad_rows<128, EPI, false>(g_dgrad_rows, dY, W, aux, dX, T, Nf, Kf, none, st);
+    else if (Kf % 64 == 0) launch_dgrad_rows<64, EPI, false>(g_dgrad_rows, dY, W, aux, dX, T, Nf, Kf, none, st);
     else return DTQN_E_UNSUPPORTED;
     prof_end(PROF_DGRAD, st, 2.0 * (double)T * Nf * Kf);
+    DTQN_LAUNCH_CHECK();
+    return 0;
+}
+
+// dgrad whose output is the dy of a LayerNorm (Kf == d_model == 64 or 128): LayerNorm backward in the epilogue
+template <int EPI>
+int launch_dgrad_ln(const float* dY, const float* W, const float* aux, int T, int Nf, int d, const LnBwdArgs& ln, cudaStream_t st) {
+    prof_begin(PROF_DGRAD, st);
+    if (d == 128) launch_dgrad_rows<128, EPI, true>(g_dgrad_rows, dY, W, aux, nullptr, T, Nf, d, ln, st);
+    else if (d == 64) launch_dgrad_rows<64, EPI, true>(g_dgrad_rows, dY, W, aux, nullptr, T, Nf, d, ln, st);
+    else return DTQN_E_UNSUPPORTED;
+    prof_end(PROF_DGRAD, st, 2.0 * (double)T * Nf * d);
     DTQN_LAUNCH_CHECK();
     return 0;
 }
@@ -562,7 +660,7 @@ int launch_wgrad(const float* dY, const float* X, int T, int Nf, int Kf, float* 
 }
 
 struct BwdScratch {
-    float *dq, *g_hh, *gx, *gu, *ga, *ga1, *gh, *gqkv, *go, *gx1, *partial;
+    float *dq, *g_hh, *gx, *gu, *ga, *ga1, *gh, *gqkv, *go, *gx1, *ga_alt, *partial;
     float *pgrad;            // [n_chunks][flat parameter count] split-K partials of the weight / bias gradients
     float *psmall;           // per-CTA partials of the head / LayerNorm / embedding gradients (one launch at a time)
     unsigned* ticket;        // [0] td loss; [1] head; [2] LayerNorm; [3] embedding; [8, 72) weight-gradient tiles
@@ -574,13 +672,14 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
     auto take = [&](long long n) { float* p = base ? base + o : nullptr; o = al4(o + n); return p; };
     s.dq = take(T0 * c.num_actions); s.g_hh = take(T0 * d); s.gx = take(T0 * d); s.gu = take(T0 * d);
     s.ga = take(T0 * d); s.ga1 = take(T0 * d); s.gh = take(T0 * 4 * d); s.gqkv = take(T0 * 3 * d); s.go = take(T0 * d); s.gx1 = take(T0 * d);
+    s.ga_alt = take(T0 * d);       // fused LayerNorm backward: da of the next layer is written before this layer's wgrad(ga) is joined
     s.partial = take((long long)dtqn_cdiv(T0, 256) * 8);
     NetLayout lay;
     net_layout(c, lay);
     s.pgrad = take((long long)dtqn_cdiv(T0, WG_CHUNK) * lay.total);
     const long long n_emb = d * lay.k_in + d + (c.discrete ? (long long)c.vocab * c.embed_per_obs : 0);
-    long long small = (long long)dtqn_cdiv(T0, HB_TOK) * (c.num_actions * d + c.num_actions);
-    if ((long long)dtqn_cdiv(T0, 32) * 2 * d > small) small = (long long)dtqn_cdiv(T0, 32) * 2 * d;
+    long long small = (long long)dtqn_cdiv(T0, HB_TOK_MIN) * (c.num_actions * d + c.num_actions);
+    if ((long long)dtqn_cdiv(T0, 16) * 2 * d > small) small = (long long)dtqn_cdiv(T0, 16) * 2 * d;   // LayerNorm: 32 (own kernel) or >= 16 rows per CTA
     if ((long long)dtqn_cdiv(T0, 32) * n_emb > small) small = (long long)dtqn_cdiv(T0, 32) * n_emb;
     s.psmall = take(small);
     s.ticket = reinterpret_cast<unsigned*>(take(72));
@@ -591,6 +690,17 @@ long long bwd_scratch_layout(const dtqn_net_cfg& c, long long T0, float* base, B
 }  // namespace
 
 extern "C" int dtqn_set_parallel_wgrad(int32_t on) { g_parallel_wgrad = on; return 0; }
+extern "C" int dtqn_set_dgrad_rows(int32_t rows) {
+    if (rows != 64 && rows != 32 && rows != 16) return DTQN_E_ARG;
+    g_dgrad_rows = rows;
+    return 0;
+}
+extern "C" int dtqn_set_head_bwd_tokens(int32_t tokens) {
+    if (tokens != 64 && tokens != 32 && tokens != 16) return DTQN_E_ARG;
+    g_head_tok = tokens;
+    return 0;
+}
+extern "C" int dtqn_set_fuse_ln_bwd(int32_t on) { g_fuse_ln_bwd = on ? 1 : 0; return 0; }
 extern "C" int dtqn_set_wgrad_chunk(int32_t tokens) {
     if (tokens < WG_CHUNK || tokens % 16) return DTQN_E_ARG;      // the partial buffer is sized for WG_CHUNK-token chunks
     g_wgrad_chunk = tokens;
@@ -647,7 +757,7 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
     DTQN_LAUNCH_CHECK();
     // head: ffn.2 then ffn.0 (group 0 rows are the first T0 rows of every activation buffer)
     prof_begin(PROF_HEAD, st);
-    launch_k(head_bwd_kernel, dtqn_cdiv(T0, HB_TOK), 256, 0, st, s.dq, (const float*)act.hh, params + lay.h2_w, Ti, d, A, s.g_hh,
+    launch_k(head_bwd_kernel, dtqn_cdiv(T0, g_head_tok), 256, 0, st, s.dq, (const float*)act.hh, params + lay.h2_w, Ti, d, A, g_head_tok, s.g_hh,
              grads + lay.h2_w, grads + lay.h2_b, s.psmall, s.ticket + 1);
     prof_end(PROF_HEAD, st, 4.0 * (double)T0 * d * A);
     DTQN_LAUNCH_CHECK();
@@ -660,33 +770,51 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
         return launch_wgrad(dY, X, Ti, Nf, Kf, grads + b_off, s.pgrad + w_off, s.pgrad + b_off, lay.total, ws_);
     };
     const float* x_last = act.layer[cfg->n_layers - 1].x2;
+    // LayerNorm backward either as its own kernel or (dtqn_set_fuse_ln_bwd) as the epilogue of the dgrad producing its dy.  Fused, the
+    // LN2 of layer li - 1 runs inside layer li's in_proj dgrad, i.e. before layer li's weight-gradient GEMMs are joined, so its da
+    // alternates between two buffers (ga / ga_alt) instead of overwriting the one wgrad(ffn.2) of layer li may still be reading.
+    const bool fuse = g_fuse_ln_bwd && (d == 64 || d == 128);
+    auto ga_of = [&](int li) { return (fuse && (li & 1)) ? s.ga_alt : s.ga; };
+    auto ln2_args = [&](int li) {
+        const LayerOff& lo = lay.layer[li];
+        const LayerAct& la = act.layer[li];
+        return LnBwdArgs{la.x1, la.r2, la.st2, params + lo.ln2_w, s.gu, ga_of(li), grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2};
+    };
     fork();
     if ((rc = wgrad(s.g_hh, x_last, d, d, lay.h1_w, lay.h1_b))) return rc;
-    if ((rc = launch_dgrad<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, s.gx, Ti, d, d, st))) return rc;
+    if (fuse) { if ((rc = launch_dgrad_ln<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, Ti, d, d, ln2_args(cfg->n_layers - 1), st))) return rc; }
+    else if ((rc = launch_dgrad<DG_NONE>(s.g_hh, params + lay.h1_w, nullptr, s.gx, Ti, d, d, st))) return rc;
     for (int li = cfg->n_layers - 1; li >= 0; --li) {
         const LayerOff& lo = lay.layer[li];
         const LayerAct& la = act.layer[li];
         const float* x_in = li == 0 ? act.x0 : act.layer[li - 1].x2;
-        // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
-        prof_begin(PROF_LN_BWD, st);
-        if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
-        else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
-        prof_end(PROF_LN_BWD, st, 0.0);
-        DTQN_LAUNCH_CHECK();
+        float* ga = ga_of(li);
+        if (!fuse) {
+            // LN2 backward: dy = gx -> gu (du2), ga (d ffn.2 output)
+            prof_begin(PROF_LN_BWD, st);
+            if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
+            else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx, la.x1, la.r2, la.st2, params + lo.ln2_w, Ti, s.gu, s.ga, grads + lo.ln2_w, grads + lo.ln2_b, s.psmall, s.ticket + 2);
+            prof_end(PROF_LN_BWD, st, 0.0);
+            DTQN_LAUNCH_CHECK();
+        }
         // ffn.2
         fork();
-        if ((rc = wgrad(s.ga, la.h, d, 4 * d, lo.f2_w, lo.f2_b))) return rc;
-        if ((rc = launch_dgrad<DG_MASK>(s.ga, params + lo.f2_w, la.h, s.gh, Ti, d, 4 * d, st))) return rc;
-        // ffn.0
+        if ((rc = wgrad(ga, la.h, d, 4 * d, lo.f2_w, lo.f2_b))) return rc;
+        if ((rc = launch_dgrad<DG_MASK>(ga, params + lo.f2_w, la.h, s.gh, Ti, d, 4 * d, st))) return rc;
+        // ffn.0, then LN1 backward: dy = gx1 = gh W + du2 -> gu (du1), ga1 (d out_proj output)
         fork();
         if ((rc = wgrad(s.gh, la.x1, 4 * d, d, lo.f1_w, lo.f1_b))) return rc;
-        if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
-        // LN1 backward: dy = gx1 -> gu (du1), ga1 (d out_proj output)
-        prof_begin(PROF_LN_BWD, st);
-        if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
-        else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
-        prof_end(PROF_LN_BWD, st, 0.0);
-        DTQN_LAUNCH_CHECK();
+        if (fuse) {
+            const LnBwdArgs ln1{x_in, la.r1, la.st1, params + lo.ln1_w, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2};
+            if ((rc = launch_dgrad_ln<DG_ADD>(s.gh, params + lo.f1_w, s.gu, Ti, 4 * d, d, ln1, st))) return rc;
+        } else {
+            if ((rc = launch_dgrad<DG_ADD>(s.gh, params + lo.f1_w, s.gu, s.gx1, Ti, 4 * d, d, st))) return rc;
+            prof_begin(PROF_LN_BWD, st);
+            if (d == 64) launch_k(ln_bwd_kernel<64>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
+            else         launch_k(ln_bwd_kernel<128>, dtqn_cdiv(T0, 32), 256, 0, st, s.gx1, x_in, la.r1, la.st1, params + lo.ln1_w, Ti, s.gu, s.ga1, grads + lo.ln1_w, grads + lo.ln1_b, s.psmall, s.ticket + 2);
+            prof_end(PROF_LN_BWD, st, 0.0);
+            DTQN_LAUNCH_CHECK();
+        }
         // out_proj
         fork();
         if ((rc = wgrad(s.ga1, la.o, d, d, lo.out_w, lo.out_b))) return rc;
@@ -704,11 +832,12 @@ extern "C" int dtqn_td_backward(const dtqn_net_cfg* cfg, const float* params, co
             prof_end(PROF_ATTN_BWD, st, 8.0 * (double)T0 * L * d);
             DTQN_LAUNCH_CHECK();
         }
-        // in_proj
+        // in_proj (+ the LN2 backward of the layer below)
         fork();
         if ((rc = wgrad(s.gqkv, x_in, 3 * d, d, lo.in_w, lo.in_b))) return rc;
-        if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
-        if (par) g_side.join(st);          // the next layer overwrites ga / gh / gqkv / ga1
+        if (fuse && li > 0) { if ((rc = launch_dgrad_ln<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, Ti, 3 * d, d, ln2_args(li - 1), st))) return rc; }
+        else if ((rc = launch_dgrad<DG_ADD>(s.gqkv, params + lo.in_w, s.gu, s.gx, Ti, 3 * d, d, st))) return rc;
+        if (par) g_side.join(st);          // the next layer overwrites gh / gqkv / ga1 (and, unfused, ga)
     }
     // every weight-gradient GEMM has been joined: chunk-ordered sum of their partials into the flat gradient
     {

@@ -278,6 +278,16 @@ int dtqn_set_wgrad_chunk(int32_t tokens);
  * completed -- same results, the next grid is scheduled while the previous one drains.  0 (default): plain stream order.
  * No reference analogue (launch-mechanism knob). */
 int dtqn_set_pdl(int32_t on);
+/* Launch-shape knobs of the backward pass (no reference analogue; results stay deterministic for any setting).
+ *  dgrad_rows 64 | 32 (default) | 16: token rows per CTA of the data-gradient GEMMs -- bitwise the same results, more CTAs
+ *    in flight for the 1 600-token training batch;
+ *  fuse_ln_bwd 1 (default) | 0: each LayerNorm backward runs as the epilogue of the data-gradient GEMM that produces its dy
+ *    (4 launches fewer for 2 layers; the dgamma / dbeta partial grouping follows the GEMM's row tile, so 32 rows reproduce
+ *    the stand-alone kernel bitwise);
+ *  head_bwd_tokens 64 | 32 | 16 (default): tokens per CTA of the Q-head backward. */
+int dtqn_set_dgrad_rows(int32_t rows);
+int dtqn_set_fuse_ln_bwd(int32_t on);
+int dtqn_set_head_bwd_tokens(int32_t tokens);
 
 /* clip_grad_norm_(params, max_norm, error_if_nonfinite=True) + Adam.step (dtqn/agents/dtqn.py:257-265,
  * dtqn/agents/dqn.py:64): grads *= grad_scale (1/world after the allreduce), total = ||grads||_2,
